@@ -1,0 +1,939 @@
+/*
+ * engine.cu -- device side of the path: unified device layout of all hosted domains, the
+ * Green-Gauss tile kernel (sm_100a), device pack / unpack, and the halo exchange pipeline.
+ *
+ * Reference functions replaced:
+ *   private_compute_gradients_gg ............ src/gradients.c:25-147   -> gg_tile_kernel
+ *   compute_gradients_gg_<variant> .......... src/gradients.c:150-335  -> run_iteration()
+ *   private_get_color_and_exchange .......... src/rangelist.c:838-889  -> stream/event pipeline
+ *   initiate_thread_comm_mpi_send / _pack ... src/threads.c:187-346    -> boundary tiles first, pack on the comm stream
+ *   exchange_dbl_copy_in / copy_out ......... src/threads.c:791-869    -> rows_gather / rows_scatter kernels
+ *   exchange_dbl_mpi_send/_post_recv/_bulk_sync/_early_recv/_async
+ *                                             src/exchange_data_mpi.c:96-543 -> grouped ncclSend/ncclRecv per peer GPU
+ *   init_threads ............................ src/threads.c:730-788    -> registers the domain; cfdp_commit builds the schedule
+ *
+ * Layout in HBM (one process = one GPU, all hosted domains concatenated):
+ *   var  [rows][7]  f64   rows = for each domain: tiles (boundary tiles first, each padded to 16 rows), then ghosts
+ *   grad [rows][21] f64
+ *   pvol [rows]     f64
+ *   blob            tile blobs (normals, halo rows, ELL adjacency), see common.h
+ *   tiles           TileDesc list: boundary tiles of all domains, then interior tiles of all domains
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <string.h>
+#include <unistd.h>
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
+#include <omp.h>
+#include "common.h"
+
+#define CUDA_CHECK(call)                                                                           \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      fprintf(stderr, "Error: '%s' [%s:%i]: %s\n", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      exit(EXIT_FAILURE);                                                                          \
+    }                                                                                              \
+  } while (0)
+
+/* ------------------------------------------------------------------------------------------
+ * NCCL, resolved at run time (the process usually has torch's bundled libnccl.so.2 loaded)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { char internal[128]; } nccl_uid;
+typedef void *nccl_comm;
+enum { NCCL_INT32 = 2, NCCL_FLOAT64 = 8 };
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(nccl_uid *) = nullptr;
+  int (*CommInitRank)(nccl_comm *, int, nccl_uid, int) = nullptr;
+  int (*CommDestroy)(nccl_comm) = nullptr;
+  int (*Send)(const void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+  int (*GroupStart)(void) = nullptr;
+  int (*GroupEnd)(void) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static void nccl_load(void)
+{
+  if (g_nccl.h) return;
+  const char *cands[] = { getenv("CFDP_NCCL_LIB"), "libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2" };
+  for (const char *c : cands) {
+    if (!c || !*c) continue;
+    g_nccl.h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) { fprintf(stderr, "Error: cannot load libnccl.so.2 (set CFDP_NCCL_LIB): %s\n", dlerror()); exit(EXIT_FAILURE); }
+#define SYM(field, name) do { *(void **)(&g_nccl.field) = dlsym(g_nccl.h, name); ASSERT(g_nccl.field != nullptr); } while (0)
+  SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+  SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+}
+#define NCCL_CHECK(call)                                                                            \
+  do {                                                                                              \
+    int r_ = (call);                                                                                \
+    if (r_ != 0) {                                                                                  \
+      fprintf(stderr, "Error: '%s' [%s:%i]: %s\n", #call, __FILE__, __LINE__, g_nccl.GetErrorString(r_)); \
+      exit(EXIT_FAILURE);                                                                           \
+    }                                                                                               \
+  } while (0)
+
+/* ------------------------------------------------------------------------------------------
+ * Engine state
+ * ---------------------------------------------------------------------------------------- */
+struct PeerPlan {
+  int proc = -1;
+  long long send_off = 0, send_rows = 0; /* row offsets into the packed send / recv buffers */
+  long long recv_off = 0, recv_rows = 0;
+};
+
+struct Engine {
+  bool configured = false, planned = false, committed = false, have_device = false;
+  int proc_rank = 0, nprocs = 0, ndomains_total = 0, per_proc = 0, device = 0;
+  int resident = 0, exact = 1;
+  std::vector<Domain *> doms;  /* hosted, by ascending domain id */
+  std::mutex mu;
+  /* options */
+  ScheduleOptions sopt;
+  /* device */
+  long long rows = 0, ntiles = 0, nbtiles = 0;
+  double *d_var = nullptr, *d_grad = nullptr, *d_pvol = nullptr;
+  unsigned char *d_blob = nullptr;
+  TileDesc *d_tiles = nullptr;
+  size_t blob_bytes = 0;
+  int smem_bytes = 0, region0_doubles = 0, block_threads = 0;
+  std::vector<int *> d_rowmap;     /* per hosted domain: [nall] global device row of host point */
+  double *d_stage = nullptr; size_t stage_bytes = 0;
+  /* exchange plan */
+  long long n_local = 0;            /* ghost rows filled from a domain hosted on this GPU */
+  uint32_t *d_loc_dst = nullptr, *d_loc_src = nullptr;
+  long long n_send = 0, n_recv = 0; /* rows packed for / unpacked from other GPUs */
+  uint32_t *d_send_rows = nullptr, *d_recv_rows = nullptr;
+  double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+  std::vector<PeerPlan> peers;
+  /* host copies of the plan (built by cfdp_plan without touching the device) */
+  std::vector<TileDesc> h_tiles;
+  std::vector<size_t> blob_base;
+  std::vector<uint32_t> h_loc_dst, h_loc_src, h_send_rows, h_recv_rows;
+  int max_nfaces = 0, max_nloc = 0, max_npts = 0; size_t max_stage = 0;
+  std::map<std::pair<int, int>, std::vector<uint32_t>> send_rows_of, recv_rows_of; /* (domain, partner) -> device rows */
+  std::vector<std::vector<int>> point_of_row; /* per hosted domain: domain-relative row -> host point (-1 padding) */
+  cudaStream_t s_comp = nullptr, s_comm = nullptr;
+  cudaEvent_t ev_b = nullptr, ev_x = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  nccl_comm comm = nullptr;
+  /* stats */
+  long long launches = 0;
+  double last_kernel_ms = 0;
+  long long nfaces = 0, nown = 0, nall = 0, tile_faces = 0, halo_refs = 0, alg_bytes = 0;
+};
+static Engine g_eng;
+
+Engine *engine_get(void) { return &g_eng; }
+int engine_proc_of_domain(int domain) { return g_eng.per_proc > 0 ? domain / g_eng.per_proc : 0; }
+int engine_num_hosted(void) { return (int)g_eng.doms.size(); }
+Domain *engine_hosted(int i) { return g_eng.doms[(size_t)i]; }
+Domain *engine_domain_by_id(int id) { for (Domain *d : g_eng.doms) if (d->id == id) return d; return nullptr; }
+Domain *engine_find_domain(const void *p) { for (Domain *d : g_eng.doms) if ((const void *)d->cd == p || (const void *)d->sd == p) return d; return nullptr; }
+
+Domain *engine_register_domain(comm_data *cd, int id)
+{
+  std::lock_guard<std::mutex> lk(g_eng.mu);
+  ASSERT(!g_eng.planned);
+  Domain *d = engine_domain_by_id(id);
+  if (!d) {
+    d = new Domain(); d->id = id; g_eng.doms.push_back(d);
+    std::sort(g_eng.doms.begin(), g_eng.doms.end(), [](Domain *a, Domain *b) { return a->id < b->id; });
+  }
+  d->cd = cd; d->sd = nullptr; d->comm_read = d->tables_done = d->threads_inited = false;
+  return d;
+}
+
+static void ensure_device(void)
+{
+  Engine &E = g_eng;
+  if (E.have_device) return;
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess || n == 0) {
+    fprintf(stderr, "Error: no CUDA device: the Green-Gauss path has no CPU fallback [%s:%i]\n", __FILE__, __LINE__);
+    exit(EXIT_FAILURE);
+  }
+  ASSERT(E.device < n);
+  CUDA_CHECK(cudaSetDevice(E.device));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&E.s_comp, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&E.s_comm, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&E.ev_b, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&E.ev_x, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreate(&E.ev_t0));
+  CUDA_CHECK(cudaEventCreate(&E.ev_t1));
+  E.have_device = true;
+}
+
+static bool device_present(void)
+{
+  static int state = -1;
+  if (state < 0) { int n = 0; state = (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0; if (!state) (void)cudaGetLastError(); }
+  return state == 1;
+}
+
+void *engine_alloc_pinned(size_t bytes)
+{
+  ASSERT(bytes > 0);
+  void *p = nullptr;
+  if (device_present() && !getenv("CFDP_NO_PINNED")) {
+    if (g_eng.configured) (void)cudaSetDevice(g_eng.device);
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) return p;
+    (void)cudaGetLastError();
+  }
+  p = malloc(bytes); /* host container only (e.g. loader tests on a machine without a GPU) */
+  ASSERT(p != NULL);
+  return p;
+}
+void engine_free_pinned(void *p) { if (p && cudaFreeHost(p) != cudaSuccess) { (void)cudaGetLastError(); free(p); } }
+
+static int env_int(const char *name, int dflt) { const char *s = getenv(name); return (s && *s) ? atoi(s) : dflt; }
+
+extern "C" int cfdp_configure(int proc_rank, int nprocs, int ndomains_total, int device)
+{
+  Engine &E = g_eng;
+  if (E.planned || !E.doms.empty()) return -1;
+  if (nprocs < 1 || proc_rank < 0 || proc_rank >= nprocs || ndomains_total < nprocs || ndomains_total % nprocs) return -2;
+  E.proc_rank = proc_rank; E.nprocs = nprocs; E.ndomains_total = ndomains_total; E.per_proc = ndomains_total / nprocs;
+  E.device = device >= 0 ? device : env_int("LOCAL_RANK", 0);
+  E.sopt.tile_points = env_int("CFDP_TILE_POINTS", 256);
+  E.sopt.max_faces = env_int("CFDP_TILE_MAX_FACES", 2688);
+  E.sopt.max_local = env_int("CFDP_TILE_MAX_LOCAL", 768);
+  E.sopt.order = env_int("CFDP_TILE_ORDER", 0);
+  E.exact = env_int("CFDP_EXACT", 1);
+  E.configured = true;
+  return 0;
+}
+
+extern "C" void cfdp_set_resident(int r) { g_eng.resident = r ? 1 : 0; }
+extern "C" void cfdp_set_exact(int x) { g_eng.exact = x ? 1 : 0; }
+
+extern "C" int cfdp_nccl_get_unique_id(void *id128)
+{
+  nccl_load();
+  nccl_uid id;
+  NCCL_CHECK(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+extern "C" int cfdp_nccl_init(const void *id128)
+{
+  Engine &E = g_eng;
+  ASSERT(E.configured);
+  if (E.nprocs == 1 || E.comm) return 0;
+  ensure_device();
+  nccl_load();
+  nccl_uid id; memcpy(&id, id128, sizeof id);
+  NCCL_CHECK(g_nccl.CommInitRank(&E.comm, E.nprocs, id, E.proc_rank));
+  return 0;
+}
+
+/* pure-C drivers (no Python plumbing): rank 0 publishes the id in a file named after the rendezvous port */
+static void nccl_file_bootstrap(void)
+{
+  Engine &E = g_eng;
+  if (E.nprocs == 1 || E.comm) return;
+  char path[512];
+  const char *f = getenv("CFDP_NCCL_ID_FILE");
+  if (f && *f) snprintf(path, sizeof path, "%s", f);
+  else snprintf(path, sizeof path, "/tmp/cfdp_nccl_id_%s_%d", getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "29500", (int)getppid());
+  nccl_uid id;
+  if (E.proc_rank == 0) {
+    cfdp_nccl_get_unique_id(&id);
+    char tmp[600]; snprintf(tmp, sizeof tmp, "%s.tmp", path);
+    FILE *fp = fopen(tmp, "wb"); ASSERT(fp != NULL);
+    ASSERT(fwrite(&id, sizeof id, 1, fp) == 1); fclose(fp);
+    ASSERT(rename(tmp, path) == 0);
+  } else {
+    FILE *fp = nullptr;
+    for (int i = 0; i < 6000 && !(fp = fopen(path, "rb")); i++) usleep(10000);
+    ASSERT(fp != NULL);
+    ASSERT(fread(&id, sizeof id, 1, fp) == 1); fclose(fp);
+  }
+  cfdp_nccl_init(&id);
+}
+
+/* setup-time exchange of int messages with other processes (comm_data.c:195-250).  Default
+ * transport: NCCL.  The host plumbing may install its own (torch.distributed / gloo on machines
+ * without a GPU) with cfdp_set_int_exchange(). */
+static cfdp_int_exchange_fn g_int_exchange = nullptr;
+extern "C" void cfdp_set_int_exchange(cfdp_int_exchange_fn fn) { g_int_exchange = fn; }
+
+void engine_exchange_ints(const std::vector<int> &peer, const std::vector<const int *> &sbuf, const std::vector<int> &scount,
+                          const std::vector<int *> &rbuf, const std::vector<int> &rcount)
+{
+  Engine &E = g_eng;
+  const size_t n = peer.size();
+  if (g_int_exchange) {
+    std::vector<const int *> sb(sbuf); std::vector<int *> rb(rbuf);
+    g_int_exchange((int)n, peer.data(), sb.data(), scount.data(), rb.data(), rcount.data());
+    return;
+  }
+  ensure_device();
+  if (!E.comm) nccl_file_bootstrap();
+  ASSERT(E.comm != nullptr);
+  std::vector<int *> dbuf(n, nullptr);
+  for (size_t i = 0; i < n; i++) {
+    const int cnt = scount[i] + rcount[i];
+    CUDA_CHECK(cudaMalloc(&dbuf[i], (size_t)(cnt > 0 ? cnt : 1) * sizeof(int)));
+    if (scount[i]) CUDA_CHECK(cudaMemcpyAsync(dbuf[i], sbuf[i], (size_t)scount[i] * sizeof(int), cudaMemcpyHostToDevice, E.s_comm));
+  }
+  NCCL_CHECK(g_nccl.GroupStart());
+  for (size_t i = 0; i < n; i++) {
+    if (scount[i]) NCCL_CHECK(g_nccl.Send(dbuf[i], (size_t)scount[i], NCCL_INT32, peer[i], E.comm, E.s_comm));
+    if (rcount[i]) NCCL_CHECK(g_nccl.Recv(dbuf[i], (size_t)rcount[i], NCCL_INT32, peer[i], E.comm, E.s_comm));
+  }
+  NCCL_CHECK(g_nccl.GroupEnd());
+  for (size_t i = 0; i < n; i++)
+    if (rcount[i]) CUDA_CHECK(cudaMemcpyAsync(rbuf[i], dbuf[i], (size_t)rcount[i] * sizeof(int), cudaMemcpyDeviceToHost, E.s_comm));
+  CUDA_CHECK(cudaStreamSynchronize(E.s_comm));
+  for (size_t i = 0; i < n; i++) CUDA_CHECK(cudaFree(dbuf[i]));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * init_threads: the reference builds its CPU schedule here (threads.c:730-788).  We register the
+ * domain; the GPU schedule of all hosted domains is built together in cfdp_commit().
+ * NTHREADS is accepted for signature compatibility and ignored.
+ * ---------------------------------------------------------------------------------------- */
+extern "C" void init_threads(comm_data *cd, solver_data *sd, int NTHREADS)
+{
+  (void)NTHREADS;
+  ASSERT(cd != NULL);
+  ASSERT(sd != NULL);
+  Domain *d = engine_find_domain(cd);
+  ASSERT(d != NULL);
+  ASSERT(!g_eng.planned);
+  ASSERT(sd->nownpoints == cd->nownpoints);
+  if (cd->ndomains > 1) ASSERT(d->tables_done); /* compute_communication_tables first */
+  d->sd = sd;
+  d->threads_inited = true;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Kernels
+ * ---------------------------------------------------------------------------------------- */
+/*
+ * One thread block per tile, one thread per own point of the tile.
+ *   1. stage the tile's face normals (read once from HBM, 16-byte loads) and the var rows of
+ *      its own points (contiguous) and halo points (gathered by device row) in shared memory;
+ *   2. every thread walks its point's ELL adjacency column (coalesced 4-byte loads), reading
+ *      normal and neighbour var from shared memory, and keeps the 7x3 sums in registers:
+ *      no atomics, fixed summation order;
+ *   3. scale by 1/volume, transpose through shared memory, 16-byte coalesced stores of the
+ *      168-byte rows.  grad is never read.
+ * EXACT: separate IEEE multiply and add (no contraction) -> bit-identical to the reference
+ * compiled without FMA and run with one thread; otherwise fused multiply-add.
+ */
+template <bool EXACT>
+__global__ void __launch_bounds__(CFDP_MAX_TILE_POINTS, 2)
+gg_tile_kernel(const TileDesc *__restrict__ tiles, const unsigned char *__restrict__ blob,
+               const double *__restrict__ var, const double *__restrict__ pvol, double *__restrict__ grad,
+               int region0_doubles)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *s_r0 = reinterpret_cast<double *>(smem_raw);  /* normals, later the output rows */
+  double *s_var = s_r0 + region0_doubles;               /* [npts + nhalo][7] */
+  const TileDesc td = tiles[blockIdx.x];
+  const unsigned char *tb = blob + td.blob;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int npts = td.npts, nhalo = td.nhalo, nfaces = td.nfaces;
+
+  { /* normals */
+    const double2 *g = reinterpret_cast<const double2 *>(tb);
+    double2 *s = reinterpret_cast<double2 *>(s_r0);
+    const int n2 = (nfaces * 3 + 1) >> 1;
+    for (int i = tid; i < n2; i += nthr) s[i] = __ldg(g + i);
+  }
+  { /* var rows of the tile's own points: contiguous, 16-byte aligned (row0 % 16 == 0) */
+    const double2 *g = reinterpret_cast<const double2 *>(var + (size_t)td.row0 * NGRAD);
+    double2 *s = reinterpret_cast<double2 *>(s_var);
+    const int n = npts * NGRAD, n2 = n >> 1;
+    for (int i = tid; i < n2; i += nthr) s[i] = __ldg(g + i);
+    if ((n & 1) && tid == 0) s_var[n - 1] = __ldg(var + (size_t)td.row0 * NGRAD + n - 1);
+  }
+  { /* var rows of the tile's halo points */
+    const uint32_t *hrows = reinterpret_cast<const uint32_t *>(tb + td.halo_off);
+    double *s = s_var + npts * NGRAD;
+    const int n = nhalo * NGRAD;
+    for (int i = tid; i < n; i += nthr) {
+      const int r = i / NGRAD, c = i - r * NGRAD;
+      s[i] = __ldg(var + (size_t)__ldg(hrows + r) * NGRAD + c);
+    }
+  }
+  __syncthreads();
+
+  double acc[NGRAD * 3];
+#pragma unroll
+  for (int k = 0; k < NGRAD * 3; k++) acc[k] = 0.0;
+  if (tid < npts) {
+    double v[NGRAD];
+#pragma unroll
+    for (int q = 0; q < NGRAD; q++) v[q] = s_var[tid * NGRAD + q];
+    const uint32_t *ell = reinterpret_cast<const uint32_t *>(tb + td.halo_off + ((nhalo * 4 + 15) & ~15)) + tid;
+    const int npad = td.npad, maxdeg = td.maxdeg;
+    uint32_t e_next = maxdeg > 0 ? __ldg(ell) : CFDP_ADJ_PAD;
+    for (int j = 0; j < maxdeg; j++) {
+      const uint32_t e = e_next;
+      e_next = (j + 1 < maxdeg) ? __ldg(ell + (size_t)(j + 1) * npad) : CFDP_ADJ_PAD;
+      if (e == CFDP_ADJ_PAD) continue;
+      const double *n = s_r0 + 3 * ((e >> 16) & 0x7FFFu);
+      const double *w = s_var + NGRAD * (e & 0xFFFFu);
+      double nx = n[0], ny = n[1], nz = n[2];
+      if (e >> 31) { nx = -nx; ny = -ny; nz = -nz; } /* this point is p1: grad[p1] -= n*val  (gradients.c:101-105) */
+      if (EXACT) {
+#pragma unroll
+        for (int q = 0; q < NGRAD; q++) {
+          const double val = __dmul_rn(0.5, __dadd_rn(v[q], w[q]));            /* gradients.c:77 */
+          acc[3 * q + 0] = __dadd_rn(acc[3 * q + 0], __dmul_rn(nx, val));
+          acc[3 * q + 1] = __dadd_rn(acc[3 * q + 1], __dmul_rn(ny, val));
+          acc[3 * q + 2] = __dadd_rn(acc[3 * q + 2], __dmul_rn(nz, val));
+        }
+      } else {
+        nx *= 0.5; ny *= 0.5; nz *= 0.5;
+#pragma unroll
+        for (int q = 0; q < NGRAD; q++) {
+          const double s = v[q] + w[q];
+          acc[3 * q + 0] = fma(nx, s, acc[3 * q + 0]);
+          acc[3 * q + 1] = fma(ny, s, acc[3 * q + 1]);
+          acc[3 * q + 2] = fma(nz, s, acc[3 * q + 2]);
+        }
+      }
+    }
+    const double tmp = __ddiv_rn(1.0, __ldg(pvol + td.row0 + tid));              /* gradients.c:138 */
+#pragma unroll
+    for (int k = 0; k < NGRAD * 3; k++) acc[k] = __dmul_rn(acc[k], tmp);
+  }
+  __syncthreads(); /* everyone is done with the normals: reuse the region for the output rows */
+  if (tid < npts) {
+#pragma unroll
+    for (int k = 0; k < NGRAD * 3; k++) s_r0[tid * (NGRAD * 3) + k] = acc[k];
+  }
+  __syncthreads();
+  {
+    double *gout = grad + (size_t)td.row0 * (NGRAD * 3);
+    const int n = npts * NGRAD * 3, n2 = n >> 1;
+    double2 *g2 = reinterpret_cast<double2 *>(gout);
+    const double2 *s2 = reinterpret_cast<const double2 *>(s_r0);
+    for (int i = tid; i < n2; i += nthr) g2[i] = s2[i];
+    if ((n & 1) && tid == 0) gout[n - 1] = s_r0[n - 1];
+  }
+}
+
+/* dst[dst_rows ? dst_rows[i] : i][:] = src[src_rows ? src_rows[i] : i][:]  -- pack / unpack /
+ * on-device halo copy (threads.c:791-869: raw copies of dim2 = 21 doubles per point) */
+__global__ void rows_copy_kernel(double *__restrict__ dst, const uint32_t *__restrict__ dst_rows,
+                                 const double *__restrict__ src, const uint32_t *__restrict__ src_rows, long long nrows, int width)
+{
+  const long long total = nrows * width;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / width; const int c = (int)(i - r * width);
+    const size_t d = (dst_rows ? (size_t)dst_rows[r] : (size_t)r) * width + c;
+    const size_t s = (src_rows ? (size_t)src_rows[r] : (size_t)r) * width + c;
+    dst[d] = src[s];
+  }
+}
+
+static void launch_rows_copy(double *dst, const uint32_t *dst_rows, const double *src, const uint32_t *src_rows,
+                             long long nrows, int width, cudaStream_t st)
+{
+  if (nrows <= 0) return;
+  const long long total = nrows * width;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  rows_copy_kernel<<<(unsigned)blocks, 256, 0, st>>>(dst, dst_rows, src, src_rows, nrows, width);
+  CUDA_CHECK(cudaGetLastError());
+  g_eng.launches++;
+}
+
+static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st)
+{
+  Engine &E = g_eng;
+  if (ntiles <= 0) return;
+  if (E.exact)
+    gg_tile_kernel<true><<<(unsigned)ntiles, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.region0_doubles);
+  else
+    gg_tile_kernel<false><<<(unsigned)ntiles, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.region0_doubles);
+  CUDA_CHECK(cudaGetLastError());
+  E.launches++;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * commit: schedules, device layout, exchange plan
+ * ---------------------------------------------------------------------------------------- */
+template <typename T>
+static T *upload(const std::vector<T> &v)
+{
+  T *d = nullptr;
+  CUDA_CHECK(cudaMalloc(&d, (v.size() ? v.size() : 1) * sizeof(T)));
+  if (!v.empty()) CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+/* host part: schedules, unified rows, tile list, exchange row lists.  No device needed. */
+extern "C" void cfdp_plan(void)
+{
+  Engine &E = g_eng;
+  if (E.planned) return;
+  ASSERT(E.configured);
+  ASSERT((int)E.doms.size() == E.per_proc);
+  for (Domain *d : E.doms) { ASSERT(d->threads_inited && d->sd != NULL); }
+  const int nh = (int)E.doms.size();
+
+  /* 1. face schedules: domains in parallel when several are hosted */
+  if (nh > 1) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < nh; i++) build_schedule(E.doms[i]->sd, E.doms[i]->cd, E.sopt, E.doms[i]->sch);
+  } else {
+    build_schedule(E.doms[0]->sd, E.doms[0]->cd, E.sopt, E.doms[0]->sch);
+  }
+
+  /* 2. unified rows and tile list: boundary tiles of all domains first */
+  E.rows = 0; E.ntiles = 0; E.nbtiles = 0; E.blob_bytes = 0;
+  for (Domain *d : E.doms) {
+    d->rowbase = E.rows; E.rows += d->sch.nrows;
+    E.ntiles += d->sch.ntiles; E.nbtiles += d->sch.nboundary;
+    E.max_nfaces = std::max(E.max_nfaces, d->sch.max_nfaces); E.max_nloc = std::max(E.max_nloc, d->sch.max_nloc);
+    for (int n : d->sch.tile_npts) E.max_npts = std::max(E.max_npts, n);
+    E.max_stage = std::max(E.max_stage, (size_t)d->sch.nall * CFDP_DIM2 * sizeof(double));
+    E.nfaces += d->sch.nfaces_computed; E.nown += d->sch.nown; E.nall += d->sch.nall;
+    E.tile_faces += d->sch.tile_faces; E.halo_refs += d->sch.halo_refs;
+    E.alg_bytes += d->sch.nfaces_computed * 32 + (long long)d->sch.nall * 56 + (long long)d->sch.nown * 176;
+  }
+  ASSERT(E.rows < 0x7FFFFFF0LL);
+  E.h_tiles.resize((size_t)E.ntiles);
+  E.blob_base.resize((size_t)nh);
+  for (int i = 0; i < nh; i++) { E.blob_base[i] = E.blob_bytes; E.blob_bytes += E.doms[i]->sch.blob.size(); }
+  long long tb = 0, ti = E.nbtiles;
+  E.point_of_row.resize((size_t)nh);
+  for (int i = 0; i < nh; i++) {
+    Domain *d = E.doms[i]; DomainSchedule &s = d->sch;
+    d->tile0_b = tb; d->tile0_i = ti;
+    for (int k = 0; k < s.ntiles; k++) {
+      TileDesc t;
+      t.row0 = (uint32_t)(d->rowbase + s.tile_row0[k]);
+      t.npts = (uint16_t)s.tile_npts[k]; t.nhalo = (uint16_t)s.tile_nhalo[k];
+      t.nfaces = (uint32_t)s.tile_nfaces[k]; t.maxdeg = (uint32_t)s.tile_maxdeg[k];
+      t.blob = (uint64_t)(E.blob_base[i] + s.tile_blob[k]);
+      t.npad = (uint32_t)align_up((size_t)s.tile_npts[k], 32);
+      t.halo_off = (uint32_t)blob_halo_off(t.nfaces);
+      /* rebase the tile's halo rows from domain-relative to device rows */
+      uint32_t *hr = (uint32_t *)(&s.blob[s.tile_blob[k]] + t.halo_off);
+      for (int j = 0; j < s.tile_nhalo[k]; j++) hr[j] += (uint32_t)d->rowbase;
+      E.h_tiles[(size_t)(k < s.nboundary ? tb++ : ti++)] = t;
+    }
+    E.point_of_row[i].assign((size_t)s.nrows, -1);
+    for (int p = 0; p < s.nall; p++) E.point_of_row[i][(size_t)s.row_of_point[p]] = p;
+  }
+  ASSERT(tb == E.nbtiles && ti == E.ntiles);
+
+  /* 3. exchange plan (thread_comm.c:27-432 / threads.c:571-726 flattened into device row lists) */
+  struct Seg { int src, dst; const std::vector<uint32_t> *rows; };
+  std::map<int, std::vector<Seg>> send_segs, recv_segs; /* by peer process */
+  for (int i = 0; i < nh; i++) {
+    Domain *d = E.doms[i]; comm_data *a = d->cd;
+    if (a->ndomains == 1) continue;
+    for (int sl = 0; sl < a->ncommdomains; sl++) {
+      const int k = a->commpartner[sl];
+      std::vector<uint32_t> &sr = E.send_rows_of[{a->iProc, k}], &rr = E.recv_rows_of[{a->iProc, k}];
+      sr.resize((size_t)a->sendcount[k]); rr.resize((size_t)a->recvcount[k]);
+      for (int j = 0; j < a->sendcount[k]; j++) sr[j] = (uint32_t)(d->rowbase + d->sch.row_of_point[a->sendindex[k][j]]);
+      for (int j = 0; j < a->recvcount[k]; j++) rr[j] = (uint32_t)(d->rowbase + d->sch.row_of_point[a->recvindex[k][j]]);
+    }
+  }
+  for (int i = 0; i < nh; i++) {
+    Domain *d = E.doms[i]; comm_data *a = d->cd;
+    if (a->ndomains == 1) continue;
+    for (int sl = 0; sl < a->ncommdomains; sl++) {
+      const int k = a->commpartner[sl];
+      if (engine_domain_by_id(k)) { /* ghost rows of a owned by k, both on this GPU: one device copy */
+        const std::vector<uint32_t> &dst = E.recv_rows_of[{a->iProc, k}], &src = E.send_rows_of[{k, a->iProc}];
+        ASSERT(dst.size() == src.size());
+        E.h_loc_dst.insert(E.h_loc_dst.end(), dst.begin(), dst.end()); E.h_loc_src.insert(E.h_loc_src.end(), src.begin(), src.end());
+      } else {
+        const int q = engine_proc_of_domain(k);
+        if (a->sendcount[k]) send_segs[q].push_back({a->iProc, k, &E.send_rows_of[{a->iProc, k}]});
+        if (a->recvcount[k]) recv_segs[q].push_back({k, a->iProc, &E.recv_rows_of[{a->iProc, k}]});
+      }
+    }
+  }
+  E.n_local = (long long)E.h_loc_dst.size();
+  std::vector<int> procs;
+  for (auto &kv : send_segs) procs.push_back(kv.first);
+  for (auto &kv : recv_segs) if (std::find(procs.begin(), procs.end(), kv.first) == procs.end()) procs.push_back(kv.first);
+  std::sort(procs.begin(), procs.end());
+  auto by_key = [](const Seg &x, const Seg &y) { return x.src != y.src ? x.src < y.src : x.dst < y.dst; };
+  for (int q : procs) {
+    PeerPlan pp; pp.proc = q;
+    pp.send_off = (long long)E.h_send_rows.size(); pp.recv_off = (long long)E.h_recv_rows.size();
+    std::vector<Seg> &ss = send_segs[q], &rs = recv_segs[q];
+    std::sort(ss.begin(), ss.end(), by_key); std::sort(rs.begin(), rs.end(), by_key); /* same order on both sides */
+    for (const Seg &sg : ss) E.h_send_rows.insert(E.h_send_rows.end(), sg.rows->begin(), sg.rows->end());
+    for (const Seg &sg : rs) E.h_recv_rows.insert(E.h_recv_rows.end(), sg.rows->begin(), sg.rows->end());
+    pp.send_rows = (long long)E.h_send_rows.size() - pp.send_off; pp.recv_rows = (long long)E.h_recv_rows.size() - pp.recv_off;
+    E.peers.push_back(pp);
+  }
+  E.n_send = (long long)E.h_send_rows.size(); E.n_recv = (long long)E.h_recv_rows.size();
+  E.planned = true;
+}
+
+/* device part: allocate, upload, configure the kernel */
+extern "C" void cfdp_commit(void)
+{
+  Engine &E = g_eng;
+  if (E.committed) return;
+  cfdp_plan();
+  ensure_device();
+  const int nh = (int)E.doms.size();
+  CUDA_CHECK(cudaMalloc(&E.d_blob, E.blob_bytes ? E.blob_bytes : 16));
+  for (int i = 0; i < nh; i++) {
+    DomainSchedule &s = E.doms[i]->sch;
+    CUDA_CHECK(cudaMemcpy(E.d_blob + E.blob_base[i], s.blob.data(), s.blob.size(), cudaMemcpyHostToDevice));
+    std::vector<unsigned char>().swap(s.blob); /* the host copy is not needed any more */
+  }
+  E.d_tiles = upload(E.h_tiles);
+
+  CUDA_CHECK(cudaMalloc(&E.d_var, (size_t)E.rows * NGRAD * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&E.d_grad, (size_t)E.rows * CFDP_DIM2 * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&E.d_pvol, (size_t)E.rows * sizeof(double)));
+  CUDA_CHECK(cudaMemset(E.d_var, 0, (size_t)E.rows * NGRAD * sizeof(double)));
+  CUDA_CHECK(cudaMemset(E.d_grad, 0, (size_t)E.rows * CFDP_DIM2 * sizeof(double)));
+  E.stage_bytes = E.max_stage;
+  CUDA_CHECK(cudaMalloc(&E.d_stage, E.stage_bytes));
+  E.d_rowmap.resize((size_t)nh);
+  {
+    std::vector<double> pv((size_t)E.rows, 1.0); /* padding rows: volume 1 */
+    for (int i = 0; i < nh; i++) {
+      Domain *d = E.doms[i]; DomainSchedule &s = d->sch;
+      std::vector<int> rm((size_t)s.nall);
+      for (int p = 0; p < s.nall; p++) { rm[p] = (int)(d->rowbase + s.row_of_point[p]); pv[(size_t)rm[p]] = d->sd->pvolume[p]; }
+      E.d_rowmap[i] = upload(rm);
+    }
+    CUDA_CHECK(cudaMemcpy(E.d_pvol, pv.data(), pv.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+
+  E.block_threads = (int)align_up((size_t)E.max_npts, 32);
+  E.region0_doubles = (int)align_up((size_t)std::max(E.max_nfaces * 3, E.max_npts * CFDP_DIM2), 2);
+  E.smem_bytes = (int)((size_t)E.region0_doubles * 8 + align_up((size_t)E.max_nloc * NGRAD * 8, 16));
+  ASSERT(E.smem_bytes <= 227 * 1024);
+  CUDA_CHECK(cudaFuncSetAttribute(gg_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+  CUDA_CHECK(cudaFuncSetAttribute(gg_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+
+  E.d_loc_dst = upload(E.h_loc_dst); E.d_loc_src = upload(E.h_loc_src);
+  E.d_send_rows = upload(E.h_send_rows); E.d_recv_rows = upload(E.h_recv_rows);
+  CUDA_CHECK(cudaMalloc(&E.d_sendbuf, (size_t)std::max<long long>(E.n_send, 1) * CFDP_DIM2 * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&E.d_recvbuf, (size_t)std::max<long long>(E.n_recv, 1) * CFDP_DIM2 * sizeof(double)));
+  if (!E.peers.empty() && !E.comm) nccl_file_bootstrap();
+  CUDA_CHECK(cudaDeviceSynchronize());
+  E.committed = true;
+  /* var as it stands in the host containers */
+  for (Domain *d : E.doms) cfdp_var_to_device(d->sd);
+  CUDA_CHECK(cudaStreamSynchronize(E.s_comp));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * host <-> device mirrors
+ * ---------------------------------------------------------------------------------------- */
+static int hosted_index(const Domain *d) { for (size_t i = 0; i < g_eng.doms.size(); i++) if (g_eng.doms[i] == d) return (int)i; return -1; }
+
+extern "C" void cfdp_var_to_device(solver_data *sd)
+{
+  Engine &E = g_eng;
+  if (!E.committed) { cfdp_commit(); return; }
+  Domain *d = engine_find_domain(sd);
+  ASSERT(d != NULL);
+  const int i = hosted_index(d);
+  const size_t n = (size_t)sd->nallpoints;
+  CUDA_CHECK(cudaMemcpyAsync(E.d_stage, &sd->var[0][0], n * NGRAD * sizeof(double), cudaMemcpyHostToDevice, E.s_comp));
+  launch_rows_copy(E.d_var, (const uint32_t *)E.d_rowmap[i], E.d_stage, nullptr, (long long)n, NGRAD, E.s_comp);
+}
+
+extern "C" void cfdp_grad_to_host(solver_data *sd)
+{
+  Engine &E = g_eng;
+  ASSERT(E.committed);
+  Domain *d = engine_find_domain(sd);
+  ASSERT(d != NULL);
+  const int i = hosted_index(d);
+  const size_t n = (size_t)sd->nallpoints;
+  launch_rows_copy(E.d_stage, nullptr, E.d_grad, (const uint32_t *)E.d_rowmap[i], (long long)n, CFDP_DIM2, E.s_comp);
+  CUDA_CHECK(cudaMemcpyAsync(&sd->grad[0][0][0], E.d_stage, n * CFDP_DIM2 * sizeof(double), cudaMemcpyDeviceToHost, E.s_comp));
+  CUDA_CHECK(cudaStreamSynchronize(E.s_comp));
+}
+
+/* grad rows of the host container that the exchange overwrites must be on the device before
+ * a drop-in call when the caller modified them: not needed, ghosts are fully rewritten */
+
+/* ------------------------------------------------------------------------------------------
+ * one iteration = gradient of all hosted domains + halo exchange of grad
+ * ---------------------------------------------------------------------------------------- */
+static bool have_exchange(void) { return g_eng.n_local > 0 || !g_eng.peers.empty(); }
+
+static void enqueue_exchange(cudaStream_t st)
+{
+  Engine &E = g_eng;
+  /* halo rows whose owner lives on this GPU: one gather/scatter, no staging */
+  launch_rows_copy(E.d_grad, E.d_loc_dst, E.d_grad, E.d_loc_src, E.n_local, CFDP_DIM2, st);
+  if (E.peers.empty()) return;
+  launch_rows_copy(E.d_sendbuf, nullptr, E.d_grad, E.d_send_rows, E.n_send, CFDP_DIM2, st);      /* threads.c:791-813 */
+  NCCL_CHECK(g_nccl.GroupStart());
+  for (const PeerPlan &p : E.peers) {                                                               /* exchange_data_mpi.c:96-166 */
+    if (p.recv_rows) NCCL_CHECK(g_nccl.Recv(E.d_recvbuf + p.recv_off * CFDP_DIM2, (size_t)p.recv_rows * CFDP_DIM2, NCCL_FLOAT64, p.proc, E.comm, st));
+    if (p.send_rows) NCCL_CHECK(g_nccl.Send(E.d_sendbuf + p.send_off * CFDP_DIM2, (size_t)p.send_rows * CFDP_DIM2, NCCL_FLOAT64, p.proc, E.comm, st));
+  }
+  NCCL_CHECK(g_nccl.GroupEnd());
+  launch_rows_copy(E.d_grad, E.d_recv_rows, E.d_recvbuf, nullptr, E.n_recv, CFDP_DIM2, st);      /* threads.c:816-839 */
+}
+
+static void run_iteration(int variant)
+{
+  Engine &E = g_eng;
+  const bool overlap = (variant == CFDP_MPI_ASYNC || variant == CFDP_GASPI_ASYNC);
+  if (variant == CFDP_COMM_FREE || !have_exchange()) {
+    launch_gradient(0, E.ntiles, E.s_comp);                       /* gradients.c:150-165 */
+  } else if (!overlap) {
+    launch_gradient(0, E.ntiles, E.s_comp);                       /* bulk synchronous: compute, then exchange (exchange_data_mpi.c:199-284) */
+    enqueue_exchange(E.s_comp);
+  } else {
+    /* early send (threads.c:253-346): tiles holding send points first, their rows are packed and
+     * shipped on the comm stream while the interior tiles compute */
+    launch_gradient(0, E.nbtiles, E.s_comp);
+    CUDA_CHECK(cudaEventRecord(E.ev_b, E.s_comp));
+    CUDA_CHECK(cudaStreamWaitEvent(E.s_comm, E.ev_b, 0));
+    enqueue_exchange(E.s_comm);
+    CUDA_CHECK(cudaEventRecord(E.ev_x, E.s_comm));
+    launch_gradient(E.nbtiles, E.ntiles - E.nbtiles, E.s_comp);
+    CUDA_CHECK(cudaStreamWaitEvent(E.s_comp, E.ev_x, 0));        /* exchange_dbl_mpi_async waits for all partners before returning */
+  }
+  for (Domain *d : E.doms)
+    if (d->cd->ndomains > 1 && variant != CFDP_COMM_FREE) { d->cd->send_stage++; d->cd->recv_stage++; d->cd->comm_stage++; }
+}
+
+extern "C" double cfdp_iterate(int variant, int niter, int final_last)
+{
+  (void)final_last; /* `final` only suppresses re-posting receives in the reference (exchange_data_mpi.c:527-531) */
+  Engine &E = g_eng;
+  cfdp_commit();
+  ASSERT(variant >= CFDP_COMM_FREE && variant <= CFDP_GASPI_ASYNC);
+  CUDA_CHECK(cudaEventRecord(E.ev_t0, E.s_comp));
+  for (int i = 0; i < niter; i++) run_iteration(variant);
+  CUDA_CHECK(cudaEventRecord(E.ev_t1, E.s_comp));
+  CUDA_CHECK(cudaEventSynchronize(E.ev_t1));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, E.ev_t0, E.ev_t1));
+  if (variant == CFDP_COMM_FREE && niter > 0) E.last_kernel_ms = ms / niter;
+  return (double)ms;
+}
+
+extern "C" double cfdp_step_e2e(int variant)
+{
+  Engine &E = g_eng;
+  cfdp_commit();
+  CUDA_CHECK(cudaEventRecord(E.ev_t0, E.s_comp));
+  for (Domain *d : E.doms) cfdp_var_to_device(d->sd);
+  run_iteration(variant);
+  for (Domain *d : E.doms) cfdp_grad_to_host(d->sd);
+  CUDA_CHECK(cudaEventRecord(E.ev_t1, E.s_comp));
+  CUDA_CHECK(cudaEventSynchronize(E.ev_t1));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, E.ev_t0, E.ev_t1));
+  return (double)ms;
+}
+
+extern "C" void cfdp_device_synchronize(void)
+{
+  if (!g_eng.have_device) return;
+  CUDA_CHECK(cudaStreamSynchronize(g_eng.s_comp));
+  CUDA_CHECK(cudaStreamSynchronize(g_eng.s_comm));
+}
+
+/* the reference-named per-domain entry points.  They may be called by every OpenMP thread of a
+ * parallel region (solver.c:45-55): only thread 0 acts. */
+static void gradients_entry(comm_data *cd, solver_data *sd, int variant, int final)
+{
+  ASSERT(cd != NULL);
+  ASSERT(sd != NULL);
+  if (omp_get_thread_num() != 0) return;
+  Engine &E = g_eng;
+  Domain *d = engine_find_domain(sd);
+  ASSERT(d != NULL && d->cd == cd);
+  cfdp_commit();
+  if (E.doms.size() != 1) {
+    /* several hosted domains advance together: the call for the first hosted domain drives all */
+    if (d != E.doms[0]) return;
+  }
+  if (!E.resident) for (Domain *x : E.doms) cfdp_var_to_device(x->sd);
+  run_iteration(cd->ndomains == 1 ? CFDP_COMM_FREE : variant);
+  (void)final;
+  if (!E.resident) for (Domain *x : E.doms) cfdp_grad_to_host(x->sd);
+}
+
+extern "C" void compute_gradients_gg_comm_free(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_COMM_FREE, final); }
+extern "C" void compute_gradients_gg_mpi_bulk_sync(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_MPI_BULK_SYNC, final); }
+extern "C" void compute_gradients_gg_mpi_early_recv(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_MPI_EARLY_RECV, final); }
+extern "C" void compute_gradients_gg_mpi_async(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_MPI_ASYNC, final); }
+extern "C" void compute_gradients_gg_gaspi_bulk_sync(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_GASPI_BULK_SYNC, final); }
+extern "C" void compute_gradients_gg_gaspi_async(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_GASPI_ASYNC, final); }
+/* one-sided MPI variants (USE_MPI_1_SIDED, exchange_data_mpidma.c): same write-then-signal data
+ * flow as the GASPI variants on this backend */
+extern "C" void compute_gradients_gg_mpifence_bulk_sync(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_GASPI_BULK_SYNC, final); }
+extern "C" void compute_gradients_gg_mpifence_async(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_GASPI_ASYNC, final); }
+extern "C" void compute_gradients_gg_mpipscw_bulk_sync(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_GASPI_BULK_SYNC, final); }
+extern "C" void compute_gradients_gg_mpipscw_async(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_GASPI_ASYNC, final); }
+
+/* exchange_data_mpi.c:134-166 pre-posts MPI_Irecv; NCCL receives are enqueued together with the
+ * sends, so this only validates its arguments */
+extern "C" void exchange_dbl_mpi_post_recv(comm_data *cd, int dim2)
+{
+  ASSERT(cd != NULL);
+  ASSERT(dim2 == CFDP_DIM2);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * introspection
+ * ---------------------------------------------------------------------------------------- */
+extern "C" void cfdp_get_stats(cfdp_stats *st)
+{
+  Engine &E = g_eng;
+  memset(st, 0, sizeof *st);
+  st->nprocs = E.configured ? E.nprocs : 0; st->proc_rank = E.proc_rank; st->ndomains_hosted = E.per_proc;
+  st->tile_points = E.sopt.tile_points;
+  if (!E.planned) return;
+  st->nfaces = E.nfaces; st->nown = E.nown; st->nall = E.nall; st->rows = E.rows;
+  st->ntiles = E.ntiles; st->nboundary_tiles = E.nbtiles; st->tile_faces = E.tile_faces; st->halo_refs = E.halo_refs;
+  st->blob_bytes = (long long)E.blob_bytes; st->send_rows_local = E.n_local; st->send_rows_remote = E.n_send;
+  st->alg_bytes = E.alg_bytes; st->h2d_bytes = E.nall * NGRAD * 8; st->d2h_bytes = E.nall * CFDP_DIM2 * 8;
+  st->launches = E.launches; st->last_kernel_ms = E.last_kernel_ms; st->smem_bytes = E.smem_bytes;
+}
+
+extern "C" int cfdp_get_schedule(const solver_data *sd, cfdp_schedule_view *v)
+{
+  Domain *d = engine_find_domain(sd);
+  if (!d || !g_eng.planned) return -1;
+  const DomainSchedule &s = d->sch;
+  v->ntiles = s.ntiles; v->nboundary_tiles = s.nboundary; v->nrows = s.nrows;
+  v->row_of_point = s.row_of_point.data(); v->tile_row0 = s.tile_row0.data(); v->tile_npts = s.tile_npts.data();
+  v->tile_nfaces = s.tile_nfaces.data(); v->tile_nhalo = s.tile_nhalo.data(); v->tile_is_boundary = s.tile_is_boundary.data();
+  return 0;
+}
+
+extern "C" int cfdp_get_tile(const solver_data *sd, int tile, int *face_ids, int *halo_points)
+{
+  Domain *d = engine_find_domain(sd);
+  if (!d || !g_eng.planned || tile < 0 || tile >= d->sch.ntiles) return -1;
+  const DomainSchedule &s = d->sch;
+  if (face_ids) memcpy(face_ids, &s.tile_face_ids[(size_t)s.tile_face_off[tile]], (size_t)s.tile_nfaces[tile] * sizeof(int));
+  if (halo_points) memcpy(halo_points, &s.tile_halo_pts[(size_t)s.tile_halo_off[tile]], (size_t)s.tile_nhalo[tile] * sizeof(int));
+  return s.tile_nfaces[tile];
+}
+
+static int rows_to_points(const Domain *d, const std::vector<uint32_t> &rows, int *points)
+{
+  const int i = hosted_index(d);
+  for (size_t j = 0; j < rows.size(); j++) points[j] = g_eng.point_of_row[(size_t)i][(size_t)(rows[j] - d->rowbase)];
+  return (int)rows.size();
+}
+extern "C" int cfdp_get_pack_list(const comm_data *cd, int partner, int *points)
+{
+  Domain *d = engine_find_domain(cd);
+  if (!d || !g_eng.planned) return -1;
+  auto it = g_eng.send_rows_of.find({d->id, partner});
+  if (it == g_eng.send_rows_of.end()) return 0;
+  return rows_to_points(d, it->second, points);
+}
+extern "C" int cfdp_get_unpack_list(const comm_data *cd, int partner, int *points)
+{
+  Domain *d = engine_find_domain(cd);
+  if (!d || !g_eng.planned) return -1;
+  auto it = g_eng.recv_rows_of.find({d->id, partner});
+  if (it == g_eng.recv_rows_of.end()) return 0;
+  return rows_to_points(d, it->second, points);
+}
+extern "C" int cfdp_get_sendbuf(const comm_data *cd, int partner, double *rows_out)
+{
+  Engine &E = g_eng;
+  Domain *d = engine_find_domain(cd);
+  if (!d || !E.committed) return -1;
+  auto it = E.send_rows_of.find({d->id, partner});
+  if (it == E.send_rows_of.end() || it->second.empty()) return 0;
+  const size_t n = it->second.size();
+  uint32_t *d_rows = upload(it->second);
+  double *d_buf = nullptr;
+  CUDA_CHECK(cudaMalloc(&d_buf, n * CFDP_DIM2 * sizeof(double)));
+  CUDA_CHECK(cudaStreamSynchronize(E.s_comm));
+  launch_rows_copy(d_buf, nullptr, E.d_grad, d_rows, (long long)n, CFDP_DIM2, E.s_comp); /* the pack kernel itself */
+  CUDA_CHECK(cudaMemcpyAsync(rows_out, d_buf, n * CFDP_DIM2 * sizeof(double), cudaMemcpyDeviceToHost, E.s_comp));
+  CUDA_CHECK(cudaStreamSynchronize(E.s_comp));
+  CUDA_CHECK(cudaFree(d_rows)); CUDA_CHECK(cudaFree(d_buf));
+  return (int)n;
+}
+
+extern "C" int cfdp_get_peer_plan(int i, int *proc, long long *send_rows, long long *recv_rows)
+{
+  Engine &E = g_eng;
+  if (!E.planned) return -1;
+  if (i < 0 || i >= (int)E.peers.size()) return (int)E.peers.size();
+  *proc = E.peers[(size_t)i].proc; *send_rows = E.peers[(size_t)i].send_rows; *recv_rows = E.peers[(size_t)i].recv_rows;
+  return (int)E.peers.size();
+}
+
+extern "C" int cfdp_get_exchange_entry(int dir, long long j, int *domain, int *point)
+{
+  Engine &E = g_eng;
+  if (!E.planned) return -1;
+  const std::vector<uint32_t> &rows = dir ? E.h_recv_rows : E.h_send_rows;
+  if (j < 0 || j >= (long long)rows.size()) return -1;
+  const long long r = rows[(size_t)j];
+  for (size_t i = 0; i < E.doms.size(); i++) {
+    Domain *d = E.doms[i];
+    if (r >= d->rowbase && r < d->rowbase + d->sch.nrows) { *domain = d->id; *point = E.point_of_row[i][(size_t)(r - d->rowbase)]; return 0; }
+  }
+  return -1;
+}
+
+extern "C" void cfdp_finalize(void)
+{
+  Engine &E = g_eng;
+  if (E.have_device) {
+    cudaDeviceSynchronize();
+    if (E.comm) { g_nccl.CommDestroy(E.comm); E.comm = nullptr; }
+    cudaFree(E.d_var); cudaFree(E.d_grad); cudaFree(E.d_pvol); cudaFree(E.d_blob); cudaFree(E.d_tiles); cudaFree(E.d_stage);
+    cudaFree(E.d_loc_dst); cudaFree(E.d_loc_src); cudaFree(E.d_send_rows); cudaFree(E.d_recv_rows); cudaFree(E.d_sendbuf); cudaFree(E.d_recvbuf);
+    for (int *p : E.d_rowmap) cudaFree(p);
+  }
+  for (Domain *d : E.doms) {
+    /* host containers this library allocated (read_solver_data / read_communication_data / cfdp_attach_mesh) */
+    if (d->sd) {
+      solver_data *sd = d->sd;
+      engine_free_pinned(sd->var); engine_free_pinned(sd->grad);
+      free(sd->fpoint); free(sd->fnormal); free(sd->pvolume); free(sd->psd_flux);
+      sd->var = nullptr; sd->grad = nullptr; sd->fpoint = nullptr; sd->fnormal = nullptr; sd->pvolume = nullptr; sd->psd_flux = nullptr;
+    }
+    if (d->cd && d->cd->ndomains > 1) {
+      comm_data *cd = d->cd;
+      if (cd->sendindex) for (int k = 0; k < cd->nProc; k++) { free(cd->sendindex[k]); free(cd->recvindex[k]); }
+      free(cd->sendindex); free(cd->recvindex); free(cd->commpartner); free(cd->sendcount); free(cd->recvcount);
+      free(cd->addpoint_owner); free(cd->addpoint_id); free(cd->local_recv_offset); free(cd->local_send_offset);
+      free(cd->remote_recv_offset); free(cd->notification); free((void *)cd->recv_flag); free((void *)cd->send_flag);
+      memset(cd, 0, sizeof *cd);
+    }
+    delete d;
+  }
+  E.doms.clear(); E.d_rowmap.clear(); E.point_of_row.clear(); E.peers.clear(); E.send_rows_of.clear(); E.recv_rows_of.clear();
+  E.d_var = E.d_grad = E.d_pvol = nullptr; E.d_blob = nullptr; E.d_tiles = nullptr; E.d_stage = nullptr;
+  E.d_loc_dst = E.d_loc_src = E.d_send_rows = E.d_recv_rows = nullptr; E.d_sendbuf = E.d_recvbuf = nullptr;
+  E.committed = false; E.planned = false; E.configured = false;
+  E.h_tiles.clear(); E.blob_base.clear(); E.h_loc_dst.clear(); E.h_loc_src.clear(); E.h_send_rows.clear(); E.h_recv_rows.clear();
+  E.max_nfaces = E.max_nloc = E.max_npts = 0; E.max_stage = 0; E.blob_bytes = 0;
+  E.rows = E.ntiles = E.nbtiles = 0; E.nfaces = E.nown = E.nall = E.tile_faces = E.halo_refs = E.alg_bytes = 0;
+  E.n_local = E.n_send = E.n_recv = 0; E.launches = 0; E.nprocs = 0; E.per_proc = 0;
+}

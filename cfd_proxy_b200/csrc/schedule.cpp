@@ -1,0 +1,343 @@
+/*
+ * schedule.cpp -- the GPU face schedule, built once at setup from the same partition.
+ *
+ * Replaces the reference's CPU schedule: thread domains (src/rangelist.c:320-398), the
+ * per-thread halo-first face sort and <=96-face colours with ftype 1/2/3
+ * (src/rangelist.c:500-764), and the first/last-touch point lists
+ * (src/points_of_color.c:26-287).  What is preserved:
+ *   - only own points are written, faces with both ends in the outer halo are dropped
+ *     (rangelist.c:513-523),
+ *   - a face cut by a tile boundary is duplicated and each copy writes only its own end:
+ *     the GPU analogue of ftype 1 / ftype 2 faces (rangelist.c:575-607, :719-736),
+ *   - tiles that hold inner-halo (send) points come first, so their gradients can be packed
+ *     and shipped while interior tiles compute (early send, threads.c:253-346),
+ *   - every own point is zero-initialised and scaled by 1/volume exactly once: it lives in
+ *     exactly one tile whose thread block owns its whole sum (eval.c:126-231 invariants).
+ *
+ * A tile = up to `tile_points` own points.  Its blob holds the normals of every face
+ * incident to a tile point (read once per tile), the device rows of the non-tile end points
+ * (halo of the tile) and a point-centric ELL adjacency: entry = neighbour's tile-local
+ * index | face slot << 16 | sign << 31.  A point's entries are sorted by the reference's
+ * single-thread face order (ttype, p1, p0) (rangelist.c:567-608, util.c:113-136), so the
+ * device sum runs over the same addends in the same order as the reference with one thread.
+ *
+ * Tiles are grown greedily over the own-point graph (BFS blobs, boundary first): the mesh
+ * files carry no coordinates, and their numbering need not have any locality.
+ */
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include <omp.h>
+#include "common.h"
+
+namespace {
+
+struct AdjEntry { int face; int nbr; }; /* nbr >= 0: this point is p0 of face; encoded sign in face's top use */
+
+struct Csr {
+  std::vector<long long> off; /* [nown+1] */
+  std::vector<int> face;      /* face id */
+  std::vector<int> nbr;       /* other endpoint (local point id) */
+  std::vector<unsigned char> sign; /* 0: point is p0 (+=), 1: point is p1 (-=) */
+};
+
+void build_csr(const solver_data *sd, Csr &g, long long &nfaces_computed)
+{
+  const int nown = sd->nownpoints, nf = sd->nfaces;
+  g.off.assign((size_t)nown + 1, 0);
+  long long nfc = 0;
+  for (int f = 0; f < nf; f++) {
+    const int p0 = sd->fpoint[f][0], p1 = sd->fpoint[f][1];
+    ASSERT(p0 >= 0 && p0 < sd->nallpoints && p1 >= 0 && p1 < sd->nallpoints);
+    if (p0 >= nown && p1 >= nown) continue;
+    nfc++;
+    if (p0 < nown) g.off[(size_t)p0 + 1]++;
+    if (p1 < nown) g.off[(size_t)p1 + 1]++;
+  }
+  nfaces_computed = nfc;
+  for (int p = 0; p < nown; p++) g.off[(size_t)p + 1] += g.off[p];
+  const long long ne = g.off[nown];
+  g.face.resize((size_t)ne); g.nbr.resize((size_t)ne); g.sign.resize((size_t)ne);
+  std::vector<long long> cur(g.off.begin(), g.off.end() - 1);
+  for (int f = 0; f < nf; f++) {
+    const int p0 = sd->fpoint[f][0], p1 = sd->fpoint[f][1];
+    if (p0 >= nown && p1 >= nown) continue;
+    if (p0 < nown) { long long e = cur[p0]++; g.face[e] = f; g.nbr[e] = p1; g.sign[e] = 0; }
+    if (p1 < nown) { long long e = cur[p1]++; g.face[e] = f; g.nbr[e] = p0; g.sign[e] = 1; }
+  }
+}
+
+struct TileBuilder {
+  const Csr &g; const ScheduleOptions &opt; int nown, nall;
+  std::vector<int> tile_of;      /* [nown] */
+  std::vector<int> halo_stamp;   /* [nall] */
+  std::vector<int> queued_stamp; /* [nown] */
+  std::vector<int> pts;          /* points in tile order, concatenated */
+  std::vector<long long> tile_pt_off;
+  /* current tile state */
+  int cur = -1, np = 0, nf = 0, nh = 0;
+
+  TileBuilder(const Csr &g_, const ScheduleOptions &o, int nown_, int nall_) : g(g_), opt(o), nown(nown_), nall(nall_)
+  {
+    tile_of.assign((size_t)nown, -1); halo_stamp.assign((size_t)nall, -1); queued_stamp.assign((size_t)nown, -1);
+    tile_pt_off.push_back(0);
+  }
+  void open() { cur = (int)tile_pt_off.size() - 1; np = nf = nh = 0; }
+  void close() { tile_pt_off.push_back((long long)pts.size()); cur = -1; }
+  /* try to add own point p to the open tile; false when a cap would be exceeded */
+  bool add(int p)
+  {
+    int in_tile = 0, new_halo = 0;
+    const long long b = g.off[p], e = g.off[(size_t)p + 1];
+    for (long long i = b; i < e; i++) {
+      const int q = g.nbr[i];
+      if (q < nown && tile_of[q] == cur) in_tile++;
+      else if (halo_stamp[q] != cur) new_halo++; /* duplicates inside one point's list are rare; over-count is safe */
+    }
+    const int was_halo = halo_stamp[p] == cur ? 1 : 0;
+    const int nf2 = nf + (int)(e - b) - in_tile;
+    const int nloc2 = np + 1 + nh + new_halo - was_halo;
+    if (np > 0 && (np + 1 > opt.tile_points || nf2 > opt.max_faces || nloc2 > opt.max_local)) return false;
+    ASSERT((int)(e - b) <= opt.max_faces && (int)(e - b) + 1 <= opt.max_local); /* a single point must fit */
+    tile_of[p] = cur; pts.push_back(p); np++; nf = nf2;
+    nh -= was_halo;
+    for (long long i = b; i < e; i++) {
+      const int q = g.nbr[i];
+      if (q < nown && tile_of[q] == cur) continue;
+      if (halo_stamp[q] != cur) { halo_stamp[q] = cur; nh++; }
+    }
+    return true;
+  }
+};
+
+} // namespace
+
+void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOptions &opt, DomainSchedule &out)
+{
+  const int nown = sd->nownpoints, nall = sd->nallpoints;
+  ASSERT(nown > 0 && nall >= nown);
+  ASSERT(opt.tile_points >= 16 && opt.tile_points <= CFDP_MAX_TILE_POINTS && opt.tile_points % 16 == 0);
+  ASSERT(opt.max_faces <= 32767 && opt.max_local <= 65534);
+  out = DomainSchedule();
+  out.nown = nown; out.nall = nall;
+
+  /* halo type: 1 own, 2 inner halo (listed in some sendindex), 3 outer halo (rangelist.c:118-148) */
+  std::vector<unsigned char> is_send((size_t)nown, 0);
+  if (cd && cd->ndomains > 1)
+    for (int i = 0; i < cd->ncommdomains; i++) {
+      const int k = cd->commpartner[i];
+      for (int j = 0; j < cd->sendcount[k]; j++) {
+        const int p = cd->sendindex[k][j];
+        ASSERT(p >= 0 && p < nown);
+        is_send[p] = 1;
+      }
+    }
+
+  Csr g;
+  build_csr(sd, g, out.nfaces_computed);
+
+  /* ---- 1. group own points into tiles ---- */
+  TileBuilder tb(g, opt, nown, nall);
+  if (opt.order == 1) {
+    tb.open();
+    for (int p = 0; p < nown; p++)
+      if (!tb.add(p)) { tb.close(); tb.open(); ASSERT(tb.add(p)); }
+    tb.close();
+  } else {
+    std::vector<int> fifoA, fifoB, q; /* seeds: send points / others; q: BFS queue of the open tile */
+    size_t headA = 0, headB = 0;
+    std::vector<int> send_list;
+    for (int p = 0; p < nown; p++) if (is_send[p]) send_list.push_back(p);
+    size_t scanA = 0; int scanB = 0;
+    for (int phase = 0; phase < 2; phase++) {
+      for (;;) {
+        /* seed */
+        int seed = -1;
+        if (phase == 0) {
+          while (headA < fifoA.size() && tb.tile_of[fifoA[headA]] >= 0) headA++;
+          if (headA < fifoA.size()) seed = fifoA[headA++];
+          else { while (scanA < send_list.size() && tb.tile_of[send_list[scanA]] >= 0) scanA++; if (scanA < send_list.size()) seed = send_list[scanA++]; }
+        } else {
+          while (headB < fifoB.size() && tb.tile_of[fifoB[headB]] >= 0) headB++;
+          if (headB < fifoB.size()) seed = fifoB[headB++];
+          else { while (scanB < nown && tb.tile_of[scanB] >= 0) scanB++; if (scanB < nown) seed = scanB++; }
+        }
+        if (seed < 0) break;
+        if (tb.cur < 0) tb.open();
+        q.clear(); size_t qh = 0;
+        q.push_back(seed); tb.queued_stamp[seed] = tb.cur;
+        bool full = false;
+        while (qh < q.size()) {
+          const int p = q[qh];
+          if (tb.tile_of[p] >= 0) { qh++; continue; }
+          if (!tb.add(p)) { full = true; break; }
+          qh++;
+          for (long long i = g.off[p]; i < g.off[(size_t)p + 1]; i++) {
+            const int r = g.nbr[i];
+            if (r < nown && tb.tile_of[r] < 0 && tb.queued_stamp[r] != tb.cur) { tb.queued_stamp[r] = tb.cur; q.push_back(r); }
+          }
+        }
+        if (full || tb.np >= opt.tile_points) {
+          /* the unvisited frontier seeds the following tiles, so they grow next to this one */
+          for (size_t i = qh; i < q.size(); i++) {
+            const int r = q[i];
+            if (tb.tile_of[r] >= 0) continue;
+            if (is_send[r]) fifoA.push_back(r); else fifoB.push_back(r);
+          }
+          tb.close();
+        }
+        /* else: component exhausted, keep filling the same tile from the next seed */
+      }
+      if (tb.cur >= 0 && tb.np > 0) tb.close(); /* boundary and interior tiles are never mixed */
+    }
+  }
+  const int ntiles = (int)tb.tile_pt_off.size() - 1;
+  ASSERT((long long)tb.pts.size() == nown);
+
+  /* ---- 2. boundary tiles first, rows ---- */
+  std::vector<int> tile_bnd((size_t)ntiles, 0), order((size_t)ntiles);
+  for (int t = 0; t < ntiles; t++)
+    for (long long i = tb.tile_pt_off[t]; i < tb.tile_pt_off[(size_t)t + 1]; i++)
+      if (is_send[tb.pts[i]]) { tile_bnd[t] = 1; break; }
+  int nb = 0;
+  for (int t = 0; t < ntiles; t++) if (tile_bnd[t]) order[nb++] = t;
+  { int k = nb; for (int t = 0; t < ntiles; t++) if (!tile_bnd[t]) order[k++] = t; }
+  out.ntiles = ntiles; out.nboundary = nb;
+  out.tile_row0.assign((size_t)ntiles + 1, 0);
+  out.tile_npts.resize(ntiles); out.tile_nfaces.resize(ntiles); out.tile_nhalo.resize(ntiles);
+  out.tile_maxdeg.resize(ntiles); out.tile_is_boundary.resize(ntiles);
+  out.row_of_point.assign((size_t)nall, -1);
+  std::vector<long long> pt_off((size_t)ntiles + 1, 0); /* into tb.pts, new tile order */
+  int row = 0;
+  for (int k = 0; k < ntiles; k++) {
+    const int t = order[k];
+    const int n = (int)(tb.tile_pt_off[(size_t)t + 1] - tb.tile_pt_off[t]);
+    out.tile_row0[k] = row; out.tile_npts[k] = n; out.tile_is_boundary[k] = tile_bnd[t];
+    pt_off[k] = tb.tile_pt_off[t];
+    for (int i = 0; i < n; i++) out.row_of_point[tb.pts[tb.tile_pt_off[t] + i]] = row + i;
+    row += (int)align_up((size_t)n, CFDP_TILE_ALIGN);
+  }
+  out.tile_row0[ntiles] = row;
+  out.ghost_row0 = row;
+  for (int p = nown; p < nall; p++) out.row_of_point[p] = row + (p - nown);
+  out.nrows = (int)align_up((size_t)row + (size_t)(nall - nown), CFDP_TILE_ALIGN);
+  std::vector<int> tile_of_new((size_t)nown); /* new tile index of each own point */
+  for (int k = 0; k < ntiles; k++)
+    for (int i = 0; i < out.tile_npts[k]; i++) tile_of_new[tb.pts[pt_off[k] + i]] = k;
+
+  /* ---- 3. face slots: one per (tile, incident face) ---- */
+  /* eslot[e] for adjacency entry e: slot of its face inside the tile of the entry's point */
+  std::vector<int> eslot(g.face.size(), -1);
+  std::vector<int> tnh((size_t)ntiles, 0), tmaxdeg((size_t)ntiles, 0);
+  const int nthreads = omp_get_max_threads();
+  std::vector<std::vector<int>> lmap_t((size_t)nthreads);
+  out.tile_face_off.assign((size_t)ntiles + 1, 0); out.tile_halo_off.assign((size_t)ntiles + 1, 0);
+  /* pass A: count faces / halo points per tile */
+#pragma omp parallel
+  {
+    std::vector<int> &lmap = lmap_t[omp_get_thread_num()];
+    lmap.assign((size_t)nall, -1);
+    std::vector<int> halo_local;
+#pragma omp for schedule(dynamic, 16)
+    for (int k = 0; k < ntiles; k++) {
+      const int n = out.tile_npts[k];
+      const int *P = &tb.pts[pt_off[k]];
+      for (int i = 0; i < n; i++) lmap[P[i]] = i;
+      int nf = 0, nh = 0, md = 0;
+      halo_local.clear();
+      for (int i = 0; i < n; i++) {
+        const int p = P[i];
+        const long long b = g.off[p], e = g.off[(size_t)p + 1];
+        md = std::max(md, (int)(e - b));
+        for (long long a = b; a < e; a++) {
+          const int q = g.nbr[a];
+          const bool q_in = q < nown && lmap[q] >= 0 && lmap[q] < n;
+          if (!q_in && lmap[q] < 0) { lmap[q] = n + nh; nh++; halo_local.push_back(q); }
+          /* the p0 side numbers the face; the p1 side numbers it only when p0 is outside the tile */
+          if (g.sign[a] == 0 || !q_in) eslot[a] = nf++;
+        }
+      }
+      for (int i = 0; i < n; i++) lmap[P[i]] = -1;
+      for (int q : halo_local) lmap[q] = -1;
+      out.tile_nfaces[k] = nf; tnh[k] = nh; tmaxdeg[k] = md;
+      ASSERT(nf <= 32767 && n + nh <= 65534);
+    }
+  }
+  for (int k = 0; k < ntiles; k++) {
+    out.tile_nhalo[k] = tnh[k]; out.tile_maxdeg[k] = tmaxdeg[k];
+    out.tile_face_off[(size_t)k + 1] = out.tile_face_off[k] + out.tile_nfaces[k];
+    out.tile_halo_off[(size_t)k + 1] = out.tile_halo_off[k] + tnh[k];
+    out.max_nfaces = std::max(out.max_nfaces, out.tile_nfaces[k]);
+    out.max_nloc = std::max(out.max_nloc, out.tile_npts[k] + tnh[k]);
+  }
+  out.tile_faces = out.tile_face_off[ntiles]; out.halo_refs = out.tile_halo_off[ntiles];
+  out.tile_face_ids.resize((size_t)out.tile_faces); out.tile_halo_pts.resize((size_t)out.halo_refs);
+  out.tile_blob.assign((size_t)ntiles + 1, 0);
+  for (int k = 0; k < ntiles; k++) {
+    const uint32_t npad = (uint32_t)align_up((size_t)out.tile_npts[k], 32);
+    out.tile_blob[(size_t)k + 1] = out.tile_blob[k] + blob_size((uint32_t)out.tile_nfaces[k], (uint32_t)tnh[k], (uint32_t)tmaxdeg[k], npad);
+  }
+  out.blob.assign((size_t)out.tile_blob[ntiles], 0);
+
+  /* pass B: emit blobs */
+#pragma omp parallel
+  {
+    std::vector<int> &lmap = lmap_t[omp_get_thread_num()];
+    struct Ent { int tt, p1, p0, face; uint32_t code; };
+    std::vector<Ent> ents;
+#pragma omp for schedule(dynamic, 16)
+    for (int k = 0; k < ntiles; k++) {
+      const int n = out.tile_npts[k], nf = out.tile_nfaces[k], nh = tnh[k], md = tmaxdeg[k];
+      const uint32_t npad = (uint32_t)align_up((size_t)n, 32);
+      const int *P = &tb.pts[pt_off[k]];
+      unsigned char *bl = &out.blob[out.tile_blob[k]];
+      double *nrm = (double *)bl;
+      uint32_t *hrows = (uint32_t *)(bl + blob_halo_off((uint32_t)nf));
+      uint32_t *ell = (uint32_t *)(bl + blob_adj_off((uint32_t)nf, (uint32_t)nh));
+      int *fids = &out.tile_face_ids[(size_t)out.tile_face_off[k]];
+      int *hpts = &out.tile_halo_pts[(size_t)out.tile_halo_off[k]];
+      for (size_t i = 0; i < (size_t)md * npad; i++) ell[i] = CFDP_ADJ_PAD;
+      for (int i = 0; i < n; i++) lmap[P[i]] = i;
+      int hcount = 0;
+      for (int i = 0; i < n; i++) {
+        const int p = P[i];
+        for (long long a = g.off[p]; a < g.off[(size_t)p + 1]; a++) {
+          const int q = g.nbr[a];
+          if (lmap[q] < 0) { lmap[q] = n + hcount; hpts[hcount] = q; hrows[hcount] = (uint32_t)out.row_of_point[q]; hcount++; }
+        }
+      }
+      ASSERT(hcount == nh);
+      for (int i = 0; i < n; i++) {
+        const int p = P[i];
+        ents.clear();
+        for (long long a = g.off[p]; a < g.off[(size_t)p + 1]; a++) {
+          const int q = g.nbr[a], f = g.face[a];
+          int slot = eslot[a];
+          if (slot < 0) { /* p is p1 of an internal face: the slot was numbered from q's (p0) side */
+            for (long long c = g.off[q]; c < g.off[(size_t)q + 1]; c++) if (g.face[c] == f) { slot = eslot[c]; break; }
+            ASSERT(slot >= 0);
+          } else {
+            fids[slot] = f;
+            nrm[3 * slot + 0] = sd->fnormal[f][0]; nrm[3 * slot + 1] = sd->fnormal[f][1]; nrm[3 * slot + 2] = sd->fnormal[f][2];
+          }
+          const int p0 = g.sign[a] ? q : p, p1 = g.sign[a] ? p : q;
+          const int h0 = p0 >= nown ? 3 : (is_send[p0] ? 2 : 1), h1 = p1 >= nown ? 3 : (is_send[p1] ? 2 : 1);
+          Ent en;
+          en.tt = ((h0 == 2 || h1 == 2) ? 0 : 3) + (h0 == 3 ? 0 : (h1 == 3 ? 1 : 2)); /* rangelist.c:567-608 with one thread */
+          en.p1 = p1; en.p0 = p0; en.face = f;
+          en.code = (uint32_t)lmap[q] | ((uint32_t)slot << 16) | ((uint32_t)g.sign[a] << 31);
+          ents.push_back(en);
+        }
+        std::sort(ents.begin(), ents.end(), [](const Ent &x, const Ent &y) {
+          if (x.tt != y.tt) return x.tt < y.tt;
+          if (x.p1 != y.p1) return x.p1 < y.p1;
+          if (x.p0 != y.p0) return x.p0 < y.p0;
+          return x.face < y.face;
+        });
+        for (size_t j = 0; j < ents.size(); j++) ell[j * npad + i] = ents[j].code;
+      }
+      for (int i = 0; i < n; i++) lmap[P[i]] = -1;
+      for (int j = 0; j < nh; j++) lmap[hpts[j]] = -1;
+    }
+  }
+}

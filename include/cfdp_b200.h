@@ -158,9 +158,22 @@ void cfdp_init_communication_domain(comm_data *cd, int domain);
 /* NCCL bootstrap for nprocs > 1: rank 0 creates the 128-byte id, the caller ships it (any transport) */
 int  cfdp_nccl_get_unique_id(void *id128);
 int  cfdp_nccl_init(const void *id128);
+/* transport of the setup-time index handshake between processes (comm_data.c:195-250: MPI_Send/MPI_Recv
+ * tag 4711).  Default: NCCL.  Messages i = 0..n-1 in list order; per peer the i-th send matches the
+ * peer's i-th receive.  scount[i] ints from sbuf[i] go to process peer[i], rcount[i] ints arrive in rbuf[i]. */
+typedef void (*cfdp_int_exchange_fn)(int n, const int *peer, const int *const *sbuf, const int *scount,
+                                     int *const *rbuf, const int *rcount);
+void cfdp_set_int_exchange(cfdp_int_exchange_fn fn);
+/* the per-peer plan of the halo exchange: for peer process index i (0..npeers-1) returns the peer's process
+ * rank and the numbers of grad rows sent / received per iteration; rows (device rows) may be NULL */
+int cfdp_get_peer_plan(int i, int *proc, long long *send_rows, long long *recv_rows);
+/* host point (domain rank, local point id) behind entry j of the packed send (dir = 0) / recv (dir = 1) buffer */
+int cfdp_get_exchange_entry(int dir, long long j, int *domain, int *point);
 /* called once after init_threads() of every hosted domain (implicit on first compute call):
  * builds the unified device layout, the pack/unpack lists and the exchange plan */
 void cfdp_commit(void);
+/* host half of cfdp_commit (face schedules, device row numbering, pack/unpack row lists); needs no GPU */
+void cfdp_plan(void);
 /* host<->device mirrors (SURVEY 8(b) ownership): var is uploaded, grad downloaded */
 void cfdp_var_to_device(solver_data *sd);
 void cfdp_grad_to_host(solver_data *sd);

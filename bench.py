@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- Green-Gauss gradient + halo exchange, faces/s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/_ref)
+
+Workload (config.workload): synthetic tetrahedral-dual box mesh (Kuhn lattice, ~7 faces/point),
+graph-partitioned into 8 domains (2x2x2 blocks); N GPUs host 8/N domains each (strong scaling:
+total work fixed).  One step = one iteration of the hot path: Green-Gauss gradients of every
+hosted domain + halo exchange of grad (variant mpi_async: boundary tiles first, exchange
+overlapped with interior tiles).  `value` = faces of all ranks * K / max-over-ranks device time,
+inputs resident in HBM.  `e2e` = the same through the drop-in call with HOST buffers: sd->var is
+copied host->device and sd->grad device->host inside the timed region every step.
+The shipped F6 meshes are not available offline; nothing here claims real-F6 numbers.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Green-Gauss grad+halo faces/s"
+UNIT = "faces/s"
+
+
+def lattice_for(mpoints: float):
+    """Cubic-ish lattice with ~mpoints million points, every edge a multiple of 16."""
+    import math
+    e = int(round((mpoints * 1e6) ** (1.0 / 3.0) / 16.0)) * 16
+    return (max(e, 32),) * 3
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="cfdp_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference (oracle/_ref) on the host cores
+# ----------------------------------------------------------------------------------------------
+def run_reference_sample(steps, warmup, mpoints=2.0, variant="mpi_async"):
+    """Times the reference's own CPU implementation (oracle/_ref/ref_harness: unmodified
+    gradients.c / exchange_data_mpi.c over the shm-MPI shim) on a bounded sample of the workload:
+    same mesh family and 8-domain partition, `mpoints` million points.  Falls back to the C
+    restatement (oracle/gg_oracle.c, 1 thread) when oracle/_ref is absent."""
+    import numpy as np
+    import cfd_proxy_b200.mesh as M
+    from oracle import oracle as O
+    ncores = os.cpu_count() or 1
+    n = lattice_for(mpoints)
+    spec = M.make_spec(n, (2, 2, 2), order="lex", jitter=0.1)
+    tmp = tempfile.mkdtemp(prefix="cfdp_ref_")
+    prefix = os.path.join(tmp, "synth")
+    if O.have_ref():
+        doms = M.write_mesh(prefix, spec, lvl=1)
+        faces = int(sum(int(((d["fpoint"][:, 0] < d["nown"]) | (d["fpoint"][:, 1] < d["nown"])).sum()) for d in doms))
+        threads = max(1, ncores // 8)
+        res = O.run_ref(prefix, 1, 8, variant, steps, os.path.join(tmp, "out"), threads=threads, repeats=max(2, 1 + (1 if warmup else 0)),
+                        timeout=1500)
+        best = max(r["time"]["best_s"] for r in res)   # slowest rank of the best repeat
+        kind, cores = "reference", min(ncores, 8 * threads)
+        sample = (f"{n[0]}x{n[1]}x{n[2]} lattice ({sum(d['nown'] for d in doms)/1e6:.2f} M points, {faces/1e6:.2f} M faces), 8 ranks x "
+                  f"{threads} OpenMP threads over the shm-MPI shim, variant {variant}, {steps} iterations, best of "
+                  f"{max(2, 1 + (1 if warmup else 0))} repeats (first repeat is the warm-up)")
+    else:
+        doms = [M.gen_domain(spec, r) for r in range(8)]
+        recv, send = O.recvsend_index(doms)
+        faces = int(sum(int(((d["fpoint"][:, 0] < d["nown"]) | (d["fpoint"][:, 1] < d["nown"])).sum()) for d in doms))
+        vars_ = [M.var_for(d) for d in doms]
+        best = 1e300
+        for rep in range(2):
+            t = time.perf_counter()
+            for _ in range(steps):
+                g = [O.gradients(d, v, is_send=O.is_send_mask(d, send[a])) for a, (d, v) in enumerate(zip(doms, vars_))]
+                O.exchange(g, recv, send)
+            best = min(best, time.perf_counter() - t)
+        kind, cores = "port", 1
+        sample = f"{n[0]}x{n[1]}x{n[2]} lattice, 8 domains serially, oracle/gg_oracle.c, {steps} iterations"
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return dict(value=faces * steps / best, unit=UNIT, cores=cores, kind=kind, sample=sample), best / steps * 1e3, faces
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cfdp", choices=["cfdp", "reference"])
+    ap.add_argument("--mpoints", type=float, default=float(os.environ.get("CFDP_BENCH_MPOINTS", "64")),
+                    help="million mesh points (default 64: BASELINE config 4 size, partitioned like config 5)")
+    ap.add_argument("--variant", default="mpi_async")
+    ap.add_argument("--order", default="lex", choices=["lex", "brick", "shuffle"])
+    ap.add_argument("--tile-points", type=int, default=None)
+    ap.add_argument("--fma", action="store_true", help="fused multiply-add instead of the reference's mul+add (not bit-exact)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-mpoints", type=float, default=2.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    n = lattice_for(args.mpoints)
+    workload = (f"synthetic tet-dual box {n[0]}x{n[1]}x{n[2]} ({n[0]*n[1]*n[2]/1e6:.1f} M points), 8 domains (2x2x2), "
+                f"{8 // max(world, 1)} domains per GPU, variant {args.variant}")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cpu, ms_step, faces = run_reference_sample(args.steps, args.warmup, mpoints=args.cpu_mpoints, variant=args.variant)
+        line = dict(metric=METRIC, value=cpu["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                    data="synthetic", impl="reference",
+                    config=dict(workload=workload, sample=cpu["sample"]),
+                    cpu_baseline=cpu,
+                    e2e=dict(value=cpu["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import cfd_proxy_b200.mesh as M
+    from cfd_proxy_b200.driver import session_from_env
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the gradient/halo path has no CPU fallback")
+    import torch.distributed as dist
+    t_setup = time.time()
+    kw = {}
+    if args.tile_points:
+        kw["tile_points"] = args.tile_points
+    S = session_from_env(8, **kw)
+    spec = M.make_spec(n, (2, 2, 2), order=args.order, brick=8, jitter=0.1, allow_big=True)
+    S.load_spec(spec)
+    S.setup()
+    S.lib.cfdp_set_exact(0 if args.fma else 1)
+    S.lib.cfdp_set_resident(1)
+    st = S.stats()
+    t_setup = time.time() - t_setup
+
+    def barrier():
+        S.lib.cfdp_device_synchronize()
+        if world > 1:
+            dist.barrier()
+        S.lib.cfdp_device_synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    faces_total = allsum(float(st.nfaces))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # ---- kernel-only (comm_free) iterations: the roofline number -------------------------------
+    S.iterate("comm_free", max(args.warmup, 3))
+    barrier()
+    ms_k = S.iterate("comm_free", args.steps) / args.steps
+    ms_k = allmax(ms_k)
+    peak, peak_src = measured_peak()
+    alg = float(st.alg_bytes)                       # per GPU (this rank)
+    achieved = alg / (ms_k * 1e-3) / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if abs(tj.get("alg_bytes", 0) - alg) / alg < 0.02:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
+
+    # ---- timed region: K iterations of grad + halo ---------------------------------------------
+    S.iterate(args.variant, max(args.warmup, 3))
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = S.stats().launches
+    ms = S.iterate(args.variant, args.steps)
+    barrier()
+    launches = S.stats().launches - l0
+    ms = allmax(ms)
+    clocks = sampler.stop() if rank == 0 else {}
+    value = faces_total * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the drop-in call with host buffers -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        S.lib.cfdp_set_resident(0)
+        e2e_steps = max(2, min(args.steps, 5))
+        S.step_e2e(args.variant)
+        barrier()
+        t0 = time.perf_counter()
+        ms_e = 0.0
+        for _ in range(e2e_steps):
+            ms_e += S.step_e2e(args.variant)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms_e = allmax(ms_e)
+        e2e = dict(value=faces_total * e2e_steps / (ms_e * 1e-3), unit=UNIT,
+                   h2d_bytes_per_step=int(allsum(float(st.h2d_bytes))), d2h_bytes_per_step=int(allsum(float(st.d2h_bytes))),
+                   steps=e2e_steps, ms_per_step=ms_e / e2e_steps, wall_ms_per_step=wall / e2e_steps * 1e3)
+        S.lib.cfdp_set_resident(1)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cpu, _, _ = run_reference_sample(25, 1, mpoints=args.cpu_mpoints, variant=args.variant)
+        except Exception as ex:  # the baseline is reported, never required
+            cpu = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="reference", sample=f"failed: {ex}")
+
+    if rank == 0:
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+            data="synthetic",
+            config=dict(workload=workload, points=int(n[0] * n[1] * n[2]), faces_per_iteration=int(faces_total),
+                        domains=8, domains_per_gpu=8 // world, point_order=args.order, tile_points=int(st.tile_points),
+                        arithmetic="fma" if args.fma else "mul+add in the reference's single-thread order (bit-exact)",
+                        l2="inputs larger than L2: %.1f GB read+written per iteration per GPU vs 126 MB L2" % (alg / 1e9),
+                        setup_s=round(t_setup, 1), tiles=int(st.ntiles), boundary_tiles=int(st.nboundary_tiles),
+                        halo_rows_on_device=int(st.send_rows_local), halo_rows_over_nvlink=int(st.send_rows_remote)),
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                          kernel="gg_tile_kernel", kernel_ms=ms_k, alg_bytes_per_launch=int(alg),
+                          alg_bytes_per_face=alg / float(st.nfaces), peak_source=peak_src,
+                          frac_of_8TBps_nominal=achieved / 8000.0, kernel_faces_per_s=float(st.nfaces) / (ms_k * 1e-3)),
+            cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
+        print(json.dumps(line))
+    S.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

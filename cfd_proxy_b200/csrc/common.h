@@ -31,11 +31,15 @@ struct TileDesc {
   uint16_t npts;       /* own points in the tile */
   uint16_t nhalo;      /* points outside the tile its faces reference */
   uint32_t nfaces;     /* face records in the tile blob */
-  uint32_t maxdeg;     /* ELL depth: max incident faces of a tile point */
-  uint64_t blob;       /* byte offset of the tile blob */
-  uint32_t npad;       /* ELL row pitch (npts rounded up to 32) */
+  uint16_t maxdeg;     /* ELL depth: max incident faces of a tile point */
+  uint16_t npad;       /* ELL row pitch (npts rounded up to 32) */
+  uint64_t blob;       /* byte offset of the tile blob (128-byte aligned) */
+  uint32_t blob_bytes; /* size of the tile blob (multiple of 128) */
   uint32_t halo_off;   /* byte offset of the halo row list inside the blob (normals come first) */
 };
+/* tile-local point index: [0,npts) own points of the tile, halo points from CFDP_HALO_BASE(npts) on
+ * (even, so that the own var rows can be fetched as one 16-byte granular bulk copy) */
+#define CFDP_HALO_BASE(npts) (((npts) + 1) & ~1)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -57,13 +61,16 @@ struct DomainSchedule {
   std::vector<int> row_of_point;        /* [nall] domain-relative device row */
   std::vector<int> tile_row0;           /* [ntiles+1] */
   std::vector<int> tile_npts, tile_nfaces, tile_nhalo, tile_maxdeg, tile_is_boundary;
+  std::vector<int> tile_nslots, tile_nhpos; /* shared-memory positions of face normals / halo rows (multiples of 16, >= the counts) */
   std::vector<uint64_t> tile_blob;      /* [ntiles+1] byte offsets into blob */
   std::vector<unsigned char> blob;      /* halo rows domain-relative until commit rebases them */
   std::vector<int> tile_face_ids;       /* concatenated original face ids in slot order */
   std::vector<long long> tile_face_off; /* [ntiles+1] */
   std::vector<int> tile_halo_pts;       /* concatenated original local point ids */
   std::vector<long long> tile_halo_off; /* [ntiles+1] */
-  int max_nfaces = 0, max_nloc = 0;     /* per-tile maxima: faces, npts+nhalo */
+  int max_nfaces = 0, max_nloc = 0;     /* per-tile maxima: faces, local points (own, even-padded, + halo) */
+  size_t max_blob = 0;                  /* largest tile blob in bytes */
+  long long lds_wavefronts_min = 0, lds_wavefronts_est = 0; /* face-walk shared-memory wavefronts: conflict free / estimated */
 };
 
 struct ScheduleOptions {
@@ -71,6 +78,9 @@ struct ScheduleOptions {
   int max_faces;       /* cap of face records per tile */
   int max_local;       /* cap of npts + nhalo */
   int order;           /* 0 = greedy graph growing, 1 = consecutive chunks of the file numbering */
+  int bank_placement;  /* 1 = place face slots and halo rows by shared-memory bank (fewer conflicts), 0 = discovery order */
+  int sort_in_tile;    /* 1 = points of a tile in ascending file numbering, 0 = in growth (BFS) order */
+  int stage_budget;    /* bytes one tile may occupy in shared memory (blob + var rows + volumes); 0 = no limit */
 };
 
 /* schedule.cpp */

@@ -29,6 +29,7 @@
 #include <vector>
 #include <omp.h>
 #include "common.h"
+#include "gg_kernels.cuh"
 
 #define CUDA_CHECK(call)                                                                           \
   do {                                                                                             \
@@ -107,6 +108,8 @@ struct Engine {
   TileDesc *d_tiles = nullptr;
   size_t blob_bytes = 0;
   int smem_bytes = 0, region0_doubles = 0, block_threads = 0;
+  int kernel_version = 2, chunk = 16, smem_v1 = 0, split = 2; ggk::PipeLayout pipe = {0, 2, 256}; uint32_t max_footprint = 0;
+  size_t max_blob = 0; int max_nhalo = 0;
   std::vector<int *> d_rowmap;     /* per hosted domain: [nall] global device row of host point */
   double *d_stage = nullptr; size_t stage_bytes = 0;
   /* exchange plan */
@@ -209,6 +212,9 @@ extern "C" int cfdp_configure(int proc_rank, int nprocs, int ndomains_total, int
   E.sopt.max_faces = env_int("CFDP_TILE_MAX_FACES", 2688);
   E.sopt.max_local = env_int("CFDP_TILE_MAX_LOCAL", 768);
   E.sopt.order = env_int("CFDP_TILE_ORDER", 0);
+  E.sopt.sort_in_tile = env_int("CFDP_SORT_IN_TILE", 1);
+  E.sopt.bank_placement = env_int("CFDP_BANK_PLACEMENT", 1);
+  E.sopt.stage_budget = env_int("CFDP_STAGE_BUDGET", 110 * 1024); /* two tiles (two CTAs or two stages) in 228 KB of shared memory per SM */
   E.exact = env_int("CFDP_EXACT", 1);
   E.configured = true;
   return 0;
@@ -322,135 +328,29 @@ extern "C" void init_threads(comm_data *cd, solver_data *sd, int NTHREADS)
 /* ------------------------------------------------------------------------------------------
  * Kernels
  * ---------------------------------------------------------------------------------------- */
-/*
- * One thread block per tile, one thread per own point of the tile.
- *   1. stage the tile's face normals (read once from HBM, 16-byte loads) and the var rows of
- *      its own points (contiguous) and halo points (gathered by device row) in shared memory;
- *   2. every thread walks its point's ELL adjacency column (coalesced 4-byte loads), reading
- *      normal and neighbour var from shared memory, and keeps the 7x3 sums in registers:
- *      no atomics, fixed summation order;
- *   3. scale by 1/volume, transpose through shared memory, 16-byte coalesced stores of the
- *      168-byte rows.  grad is never read.
- * EXACT: separate IEEE multiply and add (no contraction) -> bit-identical to the reference
- * compiled without FMA and run with one thread; otherwise fused multiply-add.
- */
-template <bool EXACT>
-__global__ void __launch_bounds__(CFDP_MAX_TILE_POINTS, 2)
-gg_tile_kernel(const TileDesc *__restrict__ tiles, const unsigned char *__restrict__ blob,
-               const double *__restrict__ var, const double *__restrict__ pvol, double *__restrict__ grad,
-               int region0_doubles)
-{
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *s_r0 = reinterpret_cast<double *>(smem_raw);  /* normals, later the output rows */
-  double *s_var = s_r0 + region0_doubles;               /* [npts + nhalo][7] */
-  const TileDesc td = tiles[blockIdx.x];
-  const unsigned char *tb = blob + td.blob;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int npts = td.npts, nhalo = td.nhalo, nfaces = td.nfaces;
-
-  { /* normals */
-    const double2 *g = reinterpret_cast<const double2 *>(tb);
-    double2 *s = reinterpret_cast<double2 *>(s_r0);
-    const int n2 = (nfaces * 3 + 1) >> 1;
-    for (int i = tid; i < n2; i += nthr) s[i] = __ldg(g + i);
-  }
-  { /* var rows of the tile's own points: contiguous, 16-byte aligned (row0 % 16 == 0) */
-    const double2 *g = reinterpret_cast<const double2 *>(var + (size_t)td.row0 * NGRAD);
-    double2 *s = reinterpret_cast<double2 *>(s_var);
-    const int n = npts * NGRAD, n2 = n >> 1;
-    for (int i = tid; i < n2; i += nthr) s[i] = __ldg(g + i);
-    if ((n & 1) && tid == 0) s_var[n - 1] = __ldg(var + (size_t)td.row0 * NGRAD + n - 1);
-  }
-  { /* var rows of the tile's halo points */
-    const uint32_t *hrows = reinterpret_cast<const uint32_t *>(tb + td.halo_off);
-    double *s = s_var + npts * NGRAD;
-    const int n = nhalo * NGRAD;
-    for (int i = tid; i < n; i += nthr) {
-      const int r = i / NGRAD, c = i - r * NGRAD;
-      s[i] = __ldg(var + (size_t)__ldg(hrows + r) * NGRAD + c);
-    }
-  }
-  __syncthreads();
-
-  double acc[NGRAD * 3];
-#pragma unroll
-  for (int k = 0; k < NGRAD * 3; k++) acc[k] = 0.0;
-  if (tid < npts) {
-    double v[NGRAD];
-#pragma unroll
-    for (int q = 0; q < NGRAD; q++) v[q] = s_var[tid * NGRAD + q];
-    const uint32_t *ell = reinterpret_cast<const uint32_t *>(tb + td.halo_off + ((nhalo * 4 + 15) & ~15)) + tid;
-    const int npad = td.npad, maxdeg = td.maxdeg;
-    uint32_t e_next = maxdeg > 0 ? __ldg(ell) : CFDP_ADJ_PAD;
-    for (int j = 0; j < maxdeg; j++) {
-      const uint32_t e = e_next;
-      e_next = (j + 1 < maxdeg) ? __ldg(ell + (size_t)(j + 1) * npad) : CFDP_ADJ_PAD;
-      if (e == CFDP_ADJ_PAD) continue;
-      const double *n = s_r0 + 3 * ((e >> 16) & 0x7FFFu);
-      const double *w = s_var + NGRAD * (e & 0xFFFFu);
-      double nx = n[0], ny = n[1], nz = n[2];
-      if (e >> 31) { nx = -nx; ny = -ny; nz = -nz; } /* this point is p1: grad[p1] -= n*val  (gradients.c:101-105) */
-      if (EXACT) {
-#pragma unroll
-        for (int q = 0; q < NGRAD; q++) {
-          const double val = __dmul_rn(0.5, __dadd_rn(v[q], w[q]));            /* gradients.c:77 */
-          acc[3 * q + 0] = __dadd_rn(acc[3 * q + 0], __dmul_rn(nx, val));
-          acc[3 * q + 1] = __dadd_rn(acc[3 * q + 1], __dmul_rn(ny, val));
-          acc[3 * q + 2] = __dadd_rn(acc[3 * q + 2], __dmul_rn(nz, val));
-        }
-      } else {
-        nx *= 0.5; ny *= 0.5; nz *= 0.5;
-#pragma unroll
-        for (int q = 0; q < NGRAD; q++) {
-          const double s = v[q] + w[q];
-          acc[3 * q + 0] = fma(nx, s, acc[3 * q + 0]);
-          acc[3 * q + 1] = fma(ny, s, acc[3 * q + 1]);
-          acc[3 * q + 2] = fma(nz, s, acc[3 * q + 2]);
-        }
-      }
-    }
-    const double tmp = __ddiv_rn(1.0, __ldg(pvol + td.row0 + tid));              /* gradients.c:138 */
-#pragma unroll
-    for (int k = 0; k < NGRAD * 3; k++) acc[k] = __dmul_rn(acc[k], tmp);
-  }
-  __syncthreads(); /* everyone is done with the normals: reuse the region for the output rows */
-  if (tid < npts) {
-#pragma unroll
-    for (int k = 0; k < NGRAD * 3; k++) s_r0[tid * (NGRAD * 3) + k] = acc[k];
-  }
-  __syncthreads();
-  {
-    double *gout = grad + (size_t)td.row0 * (NGRAD * 3);
-    const int n = npts * NGRAD * 3, n2 = n >> 1;
-    double2 *g2 = reinterpret_cast<double2 *>(gout);
-    const double2 *s2 = reinterpret_cast<const double2 *>(s_r0);
-    for (int i = tid; i < n2; i += nthr) g2[i] = s2[i];
-    if ((n & 1) && tid == 0) gout[n - 1] = s_r0[n - 1];
-  }
-}
-
 /* dst[dst_rows ? dst_rows[i] : i][:] = src[src_rows ? src_rows[i] : i][:]  -- pack / unpack /
  * on-device halo copy (threads.c:791-869: raw copies of dim2 = 21 doubles per point) */
 __global__ void rows_copy_kernel(double *__restrict__ dst, const uint32_t *__restrict__ dst_rows,
-                                 const double *__restrict__ src, const uint32_t *__restrict__ src_rows, long long nrows, int width)
+                                 const double *__restrict__ src, const uint32_t *__restrict__ src_rows, long long nrows, int width,
+                                 double scale)
 {
   const long long total = nrows * width;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / width; const int c = (int)(i - r * width);
     const size_t d = (dst_rows ? (size_t)dst_rows[r] : (size_t)r) * width + c;
     const size_t s = (src_rows ? (size_t)src_rows[r] : (size_t)r) * width + c;
-    dst[d] = src[s];
+    dst[d] = scale == 1.0 ? src[s] : __dmul_rn(src[s], scale);
   }
 }
 
 static void launch_rows_copy(double *dst, const uint32_t *dst_rows, const double *src, const uint32_t *src_rows,
-                             long long nrows, int width, cudaStream_t st)
+                             long long nrows, int width, cudaStream_t st, double scale = 1.0)
 {
   if (nrows <= 0) return;
   const long long total = nrows * width;
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  rows_copy_kernel<<<(unsigned)blocks, 256, 0, st>>>(dst, dst_rows, src, src_rows, nrows, width);
+  rows_copy_kernel<<<(unsigned)blocks, 256, 0, st>>>(dst, dst_rows, src, src_rows, nrows, width, scale);
   CUDA_CHECK(cudaGetLastError());
   g_eng.launches++;
 }
@@ -459,10 +359,20 @@ static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st)
 {
   Engine &E = g_eng;
   if (ntiles <= 0) return;
-  if (E.exact)
-    gg_tile_kernel<true><<<(unsigned)ntiles, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.region0_doubles);
-  else
-    gg_tile_kernel<false><<<(unsigned)ntiles, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.region0_doubles);
+  if (E.kernel_version == 2) {
+    const unsigned grid = (unsigned)((ntiles + E.chunk - 1) / E.chunk);
+    const int thr = E.block_threads * E.split;
+#define PIPE_LAUNCH(EX, SP, MB) ggk::gg_tile_pipe_kernel<EX, SP, MB><<<grid, thr, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.chunk, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.pipe)
+    if (E.split == 2) { if (E.exact) PIPE_LAUNCH(true, 2, 1); else PIPE_LAUNCH(false, 2, 1); }
+    else if (E.pipe.stages == 2) { if (E.exact) PIPE_LAUNCH(true, 1, 1); else PIPE_LAUNCH(false, 1, 1); }
+    else { if (E.exact) PIPE_LAUNCH(true, 1, 2); else PIPE_LAUNCH(false, 1, 2); }
+#undef PIPE_LAUNCH
+  } else {
+    if (E.exact)
+      ggk::gg_tile_kernel<true><<<(unsigned)ntiles, E.block_threads, E.smem_v1, st>>>(E.d_tiles + tile0, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.region0_doubles);
+    else
+      ggk::gg_tile_kernel<false><<<(unsigned)ntiles, E.block_threads, E.smem_v1, st>>>(E.d_tiles + tile0, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.region0_doubles);
+  }
   CUDA_CHECK(cudaGetLastError());
   E.launches++;
 }
@@ -505,6 +415,8 @@ extern "C" void cfdp_plan(void)
     E.max_nfaces = std::max(E.max_nfaces, d->sch.max_nfaces); E.max_nloc = std::max(E.max_nloc, d->sch.max_nloc);
     for (int n : d->sch.tile_npts) E.max_npts = std::max(E.max_npts, n);
     E.max_stage = std::max(E.max_stage, (size_t)d->sch.nall * CFDP_DIM2 * sizeof(double));
+    E.max_blob = std::max(E.max_blob, d->sch.max_blob);
+    for (int n : d->sch.tile_nhpos) E.max_nhalo = std::max(E.max_nhalo, n);
     E.nfaces += d->sch.nfaces_computed; E.nown += d->sch.nown; E.nall += d->sch.nall;
     E.tile_faces += d->sch.tile_faces; E.halo_refs += d->sch.halo_refs;
     E.alg_bytes += d->sch.nfaces_computed * 32 + (long long)d->sch.nall * 56 + (long long)d->sch.nown * 176;
@@ -521,14 +433,16 @@ extern "C" void cfdp_plan(void)
     for (int k = 0; k < s.ntiles; k++) {
       TileDesc t;
       t.row0 = (uint32_t)(d->rowbase + s.tile_row0[k]);
-      t.npts = (uint16_t)s.tile_npts[k]; t.nhalo = (uint16_t)s.tile_nhalo[k];
-      t.nfaces = (uint32_t)s.tile_nfaces[k]; t.maxdeg = (uint32_t)s.tile_maxdeg[k];
+      t.npts = (uint16_t)s.tile_npts[k]; t.nhalo = (uint16_t)s.tile_nhpos[k];     /* positions, gaps hold 0xFFFFFFFF */
+      t.nfaces = (uint32_t)s.tile_nslots[k]; t.maxdeg = (uint16_t)s.tile_maxdeg[k];
       t.blob = (uint64_t)(E.blob_base[i] + s.tile_blob[k]);
-      t.npad = (uint32_t)align_up((size_t)s.tile_npts[k], 32);
+      t.blob_bytes = (uint32_t)(s.tile_blob[(size_t)k + 1] - s.tile_blob[k]);
+      t.npad = (uint16_t)align_up((size_t)s.tile_npts[k], 32);
       t.halo_off = (uint32_t)blob_halo_off(t.nfaces);
       /* rebase the tile's halo rows from domain-relative to device rows */
       uint32_t *hr = (uint32_t *)(&s.blob[s.tile_blob[k]] + t.halo_off);
-      for (int j = 0; j < s.tile_nhalo[k]; j++) hr[j] += (uint32_t)d->rowbase;
+      for (int j = 0; j < s.tile_nhpos[k]; j++) if (hr[j] != 0xFFFFFFFFu) hr[j] += (uint32_t)d->rowbase;
+      E.max_footprint = std::max(E.max_footprint, ggk::tile_footprint(t.blob_bytes, t.npts, t.nhalo));
       E.h_tiles[(size_t)(k < s.nboundary ? tb++ : ti++)] = t;
     }
     E.point_of_row[i].assign((size_t)s.nrows, -1);
@@ -621,12 +535,38 @@ extern "C" void cfdp_commit(void)
     CUDA_CHECK(cudaMemcpy(E.d_pvol, pv.data(), pv.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
 
-  E.block_threads = (int)align_up((size_t)E.max_npts, 32);
+  E.block_threads = (int)std::max(align_up((size_t)E.max_npts, 32), align_up(((size_t)E.max_nhalo + CFDP_HALO_PER_THREAD - 1) / CFDP_HALO_PER_THREAD, 32));
+  ASSERT(E.block_threads <= CFDP_MAX_TILE_POINTS);
+  /* v1 (one tile per CTA) */
   E.region0_doubles = (int)align_up((size_t)std::max(E.max_nfaces * 3, E.max_npts * CFDP_DIM2), 2);
-  E.smem_bytes = (int)((size_t)E.region0_doubles * 8 + align_up((size_t)E.max_nloc * NGRAD * 8, 16));
-  ASSERT(E.smem_bytes <= 227 * 1024);
-  CUDA_CHECK(cudaFuncSetAttribute(gg_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
-  CUDA_CHECK(cudaFuncSetAttribute(gg_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+  E.smem_v1 = (int)((size_t)E.region0_doubles * 8 + align_up((size_t)E.max_nloc * NGRAD * 8, 16));
+  /* v2 (pipelined): two stages of [blob | var rows | volumes] */
+  E.pipe.stage_bytes = E.max_footprint;
+  E.kernel_version = env_int("CFDP_KERNEL", 2);
+  E.chunk = std::min(CFDP_MAX_CHUNK, std::max(1, env_int("CFDP_CHUNK", 16)));
+  E.split = env_int("CFDP_SPLIT", 1) == 2 ? 2 : 1;
+  E.pipe.stages = env_int("CFDP_STAGES", 1) == 2 ? 2 : 1;
+  E.pipe.block_points = E.block_threads;
+  if (E.pipe.stages == 1) E.split = 1; /* single-stage relies on two resident CTAs: 128 registers per thread at most */
+  const int smem_limit = 227 * 1024 - 256;
+  if (E.kernel_version == 2 && E.pipe.stages == 2 && 2 * (int)E.pipe.stage_bytes > smem_limit) E.pipe.stages = 1;
+  if (E.kernel_version == 2 && (int)E.pipe.stage_bytes > smem_limit) {
+    fprintf(stderr, "cfdp: pipelined kernel needs %u B of shared memory per stage, falling back to the one-tile-per-CTA kernel "
+                    "(lower CFDP_TILE_POINTS to avoid this)\n", E.pipe.stage_bytes);
+    E.kernel_version = 1;
+  }
+  ASSERT(E.smem_v1 <= smem_limit);
+  E.smem_bytes = E.kernel_version == 2 ? E.pipe.stages * (int)E.pipe.stage_bytes : E.smem_v1;
+  CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
+  CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
+  if (E.kernel_version == 2) {
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+  }
 
   E.d_loc_dst = upload(E.h_loc_dst); E.d_loc_src = upload(E.h_loc_src);
   E.d_send_rows = upload(E.h_send_rows); E.d_recv_rows = upload(E.h_recv_rows);
@@ -654,7 +594,8 @@ extern "C" void cfdp_var_to_device(solver_data *sd)
   const int i = hosted_index(d);
   const size_t n = (size_t)sd->nallpoints;
   CUDA_CHECK(cudaMemcpyAsync(E.d_stage, &sd->var[0][0], n * NGRAD * sizeof(double), cudaMemcpyHostToDevice, E.s_comp));
-  launch_rows_copy(E.d_var, (const uint32_t *)E.d_rowmap[i], E.d_stage, nullptr, (long long)n, NGRAD, E.s_comp);
+  /* the device keeps hvar = 0.5*var in tile order (exact: power-of-two scaling), see gg_kernels.cuh */
+  launch_rows_copy(E.d_var, (const uint32_t *)E.d_rowmap[i], E.d_stage, nullptr, (long long)n, NGRAD, E.s_comp, 0.5);
 }
 
 extern "C" void cfdp_grad_to_host(solver_data *sd)
@@ -812,6 +753,7 @@ extern "C" void cfdp_get_stats(cfdp_stats *st)
   st->ntiles = E.ntiles; st->nboundary_tiles = E.nbtiles; st->tile_faces = E.tile_faces; st->halo_refs = E.halo_refs;
   st->blob_bytes = (long long)E.blob_bytes; st->send_rows_local = E.n_local; st->send_rows_remote = E.n_send;
   st->alg_bytes = E.alg_bytes; st->h2d_bytes = E.nall * NGRAD * 8; st->d2h_bytes = E.nall * CFDP_DIM2 * 8;
+  for (Domain *d : E.doms) { st->lds_wavefronts_min += d->sch.lds_wavefronts_min; st->lds_wavefronts_est += d->sch.lds_wavefronts_est; }
   st->launches = E.launches; st->last_kernel_ms = E.last_kernel_ms; st->smem_bytes = E.smem_bytes;
 }
 
@@ -933,7 +875,7 @@ extern "C" void cfdp_finalize(void)
   E.d_loc_dst = E.d_loc_src = E.d_send_rows = E.d_recv_rows = nullptr; E.d_sendbuf = E.d_recvbuf = nullptr;
   E.committed = false; E.planned = false; E.configured = false;
   E.h_tiles.clear(); E.blob_base.clear(); E.h_loc_dst.clear(); E.h_loc_src.clear(); E.h_send_rows.clear(); E.h_recv_rows.clear();
-  E.max_nfaces = E.max_nloc = E.max_npts = 0; E.max_stage = 0; E.blob_bytes = 0;
+  E.max_nfaces = E.max_nloc = E.max_npts = 0; E.max_stage = 0; E.blob_bytes = 0; E.max_blob = 0; E.max_nhalo = 0; E.max_footprint = 0;
   E.rows = E.ntiles = E.nbtiles = 0; E.nfaces = E.nown = E.nall = E.tile_faces = E.halo_refs = E.alg_bytes = 0;
   E.n_local = E.n_send = E.n_recv = 0; E.launches = 0; E.nprocs = 0; E.per_proc = 0;
 }

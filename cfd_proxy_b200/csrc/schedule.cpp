@@ -75,14 +75,22 @@ struct TileBuilder {
   std::vector<int> pts;          /* points in tile order, concatenated */
   std::vector<long long> tile_pt_off;
   /* current tile state */
-  int cur = -1, np = 0, nf = 0, nh = 0;
+  int cur = -1, np = 0, nf = 0, nh = 0, md = 0;
 
   TileBuilder(const Csr &g_, const ScheduleOptions &o, int nown_, int nall_) : g(g_), opt(o), nown(nown_), nall(nall_)
   {
     tile_of.assign((size_t)nown, -1); halo_stamp.assign((size_t)nall, -1); queued_stamp.assign((size_t)nown, -1);
     tile_pt_off.push_back(0);
   }
-  void open() { cur = (int)tile_pt_off.size() - 1; np = nf = nh = 0; }
+  void open() { cur = (int)tile_pt_off.size() - 1; np = nf = nh = md = 0; }
+  /* shared-memory footprint of a tile: blob (normals, halo rows, ELL) + var rows + volumes */
+  size_t footprint(int np_, int nf_, int nh_, int md_) const
+  {
+    const uint32_t npad = (uint32_t)align_up((size_t)np_, 32);
+    nf_ = (int)align_up((size_t)nf_, 16); nh_ = (int)align_up((size_t)nh_, 16);
+    return align_up(std::max(blob_size((uint32_t)nf_, (uint32_t)nh_, (uint32_t)md_, npad), (size_t)np_ * CFDP_DIM2 * 8), 128) +
+           align_up((size_t)(CFDP_HALO_BASE(np_) + nh_) * NGRAD * 8, 128) + align_up((size_t)CFDP_HALO_BASE(np_) * 8, 128);
+  }
   void close() { tile_pt_off.push_back((long long)pts.size()); cur = -1; }
   /* try to add own point p to the open tile; false when a cap would be exceeded */
   bool add(int p)
@@ -97,9 +105,11 @@ struct TileBuilder {
     const int was_halo = halo_stamp[p] == cur ? 1 : 0;
     const int nf2 = nf + (int)(e - b) - in_tile;
     const int nloc2 = np + 1 + nh + new_halo - was_halo;
+    const int md2 = std::max(md, (int)(e - b));
     if (np > 0 && (np + 1 > opt.tile_points || nf2 > opt.max_faces || nloc2 > opt.max_local)) return false;
+    if (np > 0 && opt.stage_budget > 0 && footprint(np + 1, nf2, nloc2 - (np + 1), md2) > (size_t)opt.stage_budget) return false;
     ASSERT((int)(e - b) <= opt.max_faces && (int)(e - b) + 1 <= opt.max_local); /* a single point must fit */
-    tile_of[p] = cur; pts.push_back(p); np++; nf = nf2;
+    tile_of[p] = cur; pts.push_back(p); np++; nf = nf2; md = md2;
     nh -= was_halo;
     for (long long i = b; i < e; i++) {
       const int q = g.nbr[i];
@@ -193,6 +203,12 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
   }
   const int ntiles = (int)tb.tile_pt_off.size() - 1;
   ASSERT((long long)tb.pts.size() == nown);
+  /* inside a tile keep the file's numbering: where it has structure (neighbour id = own id + const), the
+   * lanes of a warp then walk neighbouring rows of shared memory and bank conflicts drop */
+  if (opt.sort_in_tile) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int t = 0; t < ntiles; t++) std::sort(tb.pts.begin() + tb.tile_pt_off[t], tb.pts.begin() + tb.tile_pt_off[(size_t)t + 1]);
+  }
 
   /* ---- 2. boundary tiles first, rows ---- */
   std::vector<int> tile_bnd((size_t)ntiles, 0), order((size_t)ntiles);
@@ -225,10 +241,12 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
   for (int k = 0; k < ntiles; k++)
     for (int i = 0; i < out.tile_npts[k]; i++) tile_of_new[tb.pts[pt_off[k] + i]] = k;
 
-  /* ---- 3. face slots: one per (tile, incident face) ---- */
-  /* eslot[e] for adjacency entry e: slot of its face inside the tile of the entry's point */
+  /* ---- 3. per tile: face ids, halo points ---- */
+  /* eslot[e] for adjacency entry e: tile-local id of its face inside the tile of the entry's point
+   * (ids in discovery order; the shared-memory slot is chosen later) */
   std::vector<int> eslot(g.face.size(), -1);
   std::vector<int> tnh((size_t)ntiles, 0), tmaxdeg((size_t)ntiles, 0);
+  out.tile_nslots.assign((size_t)ntiles, 0); out.tile_nhpos.assign((size_t)ntiles, 0);
   const int nthreads = omp_get_max_threads();
   std::vector<std::vector<int>> lmap_t((size_t)nthreads);
   out.tile_face_off.assign((size_t)ntiles + 1, 0); out.tile_halo_off.assign((size_t)ntiles + 1, 0);
@@ -260,72 +278,84 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
       for (int i = 0; i < n; i++) lmap[P[i]] = -1;
       for (int q : halo_local) lmap[q] = -1;
       out.tile_nfaces[k] = nf; tnh[k] = nh; tmaxdeg[k] = md;
-      ASSERT(nf <= 32767 && n + nh <= 65534);
+      /* shared-memory positions: 16 residue classes of equal size, so that slots / rows can be placed by bank */
+      out.tile_nslots[k] = (int)align_up((size_t)nf, 16); out.tile_nhpos[k] = (int)align_up((size_t)nh, 16);
+      ASSERT(out.tile_nslots[k] <= 32767 && n + 1 + out.tile_nhpos[k] <= 65534);
     }
   }
   for (int k = 0; k < ntiles; k++) {
     out.tile_nhalo[k] = tnh[k]; out.tile_maxdeg[k] = tmaxdeg[k];
     out.tile_face_off[(size_t)k + 1] = out.tile_face_off[k] + out.tile_nfaces[k];
     out.tile_halo_off[(size_t)k + 1] = out.tile_halo_off[k] + tnh[k];
-    out.max_nfaces = std::max(out.max_nfaces, out.tile_nfaces[k]);
-    out.max_nloc = std::max(out.max_nloc, out.tile_npts[k] + tnh[k]);
+    out.max_nfaces = std::max(out.max_nfaces, out.tile_nslots[k]);
+    out.max_nloc = std::max(out.max_nloc, CFDP_HALO_BASE(out.tile_npts[k]) + out.tile_nhpos[k]);
   }
   out.tile_faces = out.tile_face_off[ntiles]; out.halo_refs = out.tile_halo_off[ntiles];
   out.tile_face_ids.resize((size_t)out.tile_faces); out.tile_halo_pts.resize((size_t)out.halo_refs);
   out.tile_blob.assign((size_t)ntiles + 1, 0);
   for (int k = 0; k < ntiles; k++) {
     const uint32_t npad = (uint32_t)align_up((size_t)out.tile_npts[k], 32);
-    out.tile_blob[(size_t)k + 1] = out.tile_blob[k] + blob_size((uint32_t)out.tile_nfaces[k], (uint32_t)tnh[k], (uint32_t)tmaxdeg[k], npad);
+    const size_t bs = blob_size((uint32_t)out.tile_nslots[k], (uint32_t)out.tile_nhpos[k], (uint32_t)tmaxdeg[k], npad);
+    out.tile_blob[(size_t)k + 1] = out.tile_blob[k] + bs;
+    out.max_blob = std::max(out.max_blob, bs);
   }
   out.blob.assign((size_t)out.tile_blob[ntiles], 0);
 
-  /* pass B: emit blobs */
-#pragma omp parallel
+  /* pass B: order every point's faces, place face slots and halo rows by shared-memory bank, emit blobs */
+  const bool place_by_bank = opt.bank_placement != 0;
+  long long wf_min_total = 0, wf_est_total = 0;
+#pragma omp parallel reduction(+ : wf_min_total, wf_est_total)
   {
     std::vector<int> &lmap = lmap_t[omp_get_thread_num()];
-    struct Ent { int tt, p1, p0, face; uint32_t code; };
-    std::vector<Ent> ents;
+    struct Ent { int tt, p1, p0, face; int nbr; /* tile-local: own i or n + halo k */ int fid; uint32_t sign; };
+    std::vector<Ent> ents, tile_ents;            /* tile_ents[i*md + j] */
+    std::vector<int> deg, slot_of, hpos_of;      /* fid -> slot, halo k -> position */
+    std::vector<unsigned char> cntv, cntn;       /* [group][16] */
+    std::vector<int> grp_off, grp_list;          /* per face / per halo point: distinct groups */
 #pragma omp for schedule(dynamic, 16)
     for (int k = 0; k < ntiles; k++) {
       const int n = out.tile_npts[k], nf = out.tile_nfaces[k], nh = tnh[k], md = tmaxdeg[k];
+      const int nslots = out.tile_nslots[k], nhpos = out.tile_nhpos[k], n_even = CFDP_HALO_BASE(n);
       const uint32_t npad = (uint32_t)align_up((size_t)n, 32);
       const int *P = &tb.pts[pt_off[k]];
       unsigned char *bl = &out.blob[out.tile_blob[k]];
       double *nrm = (double *)bl;
-      uint32_t *hrows = (uint32_t *)(bl + blob_halo_off((uint32_t)nf));
-      uint32_t *ell = (uint32_t *)(bl + blob_adj_off((uint32_t)nf, (uint32_t)nh));
+      uint32_t *hrows = (uint32_t *)(bl + blob_halo_off((uint32_t)nslots));
+      uint32_t *ell = (uint32_t *)(bl + blob_adj_off((uint32_t)nslots, (uint32_t)nhpos));
       int *fids = &out.tile_face_ids[(size_t)out.tile_face_off[k]];
       int *hpts = &out.tile_halo_pts[(size_t)out.tile_halo_off[k]];
       for (size_t i = 0; i < (size_t)md * npad; i++) ell[i] = CFDP_ADJ_PAD;
+      for (int j = 0; j < nhpos; j++) hrows[j] = 0xFFFFFFFFu;
       for (int i = 0; i < n; i++) lmap[P[i]] = i;
       int hcount = 0;
       for (int i = 0; i < n; i++) {
         const int p = P[i];
         for (long long a = g.off[p]; a < g.off[(size_t)p + 1]; a++) {
           const int q = g.nbr[a];
-          if (lmap[q] < 0) { lmap[q] = n + hcount; hpts[hcount] = q; hrows[hcount] = (uint32_t)out.row_of_point[q]; hcount++; }
+          if (lmap[q] < 0) { lmap[q] = n + hcount; hpts[hcount] = q; hcount++; }
         }
       }
       ASSERT(hcount == nh);
+      /* sorted entry lists */
+      tile_ents.assign((size_t)n * md, Ent{0, 0, 0, -1, -1, -1, 0});
+      deg.assign((size_t)n, 0);
       for (int i = 0; i < n; i++) {
         const int p = P[i];
         ents.clear();
         for (long long a = g.off[p]; a < g.off[(size_t)p + 1]; a++) {
           const int q = g.nbr[a], f = g.face[a];
-          int slot = eslot[a];
-          if (slot < 0) { /* p is p1 of an internal face: the slot was numbered from q's (p0) side */
-            for (long long c = g.off[q]; c < g.off[(size_t)q + 1]; c++) if (g.face[c] == f) { slot = eslot[c]; break; }
-            ASSERT(slot >= 0);
+          int fid = eslot[a];
+          if (fid < 0) { /* p is p1 of an internal face: numbered from q's (p0) side */
+            for (long long c = g.off[q]; c < g.off[(size_t)q + 1]; c++) if (g.face[c] == f && eslot[c] >= 0) { fid = eslot[c]; break; }
+            ASSERT(fid >= 0);
           } else {
-            fids[slot] = f;
-            nrm[3 * slot + 0] = sd->fnormal[f][0]; nrm[3 * slot + 1] = sd->fnormal[f][1]; nrm[3 * slot + 2] = sd->fnormal[f][2];
+            fids[fid] = f;
           }
           const int p0 = g.sign[a] ? q : p, p1 = g.sign[a] ? p : q;
           const int h0 = p0 >= nown ? 3 : (is_send[p0] ? 2 : 1), h1 = p1 >= nown ? 3 : (is_send[p1] ? 2 : 1);
           Ent en;
           en.tt = ((h0 == 2 || h1 == 2) ? 0 : 3) + (h0 == 3 ? 0 : (h1 == 3 ? 1 : 2)); /* rangelist.c:567-608 with one thread */
-          en.p1 = p1; en.p0 = p0; en.face = f;
-          en.code = (uint32_t)lmap[q] | ((uint32_t)slot << 16) | ((uint32_t)g.sign[a] << 31);
+          en.p1 = p1; en.p0 = p0; en.face = f; en.nbr = lmap[q]; en.fid = fid; en.sign = g.sign[a];
           ents.push_back(en);
         }
         std::sort(ents.begin(), ents.end(), [](const Ent &x, const Ent &y) {
@@ -334,10 +364,130 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
           if (x.p0 != y.p0) return x.p0 < y.p0;
           return x.face < y.face;
         });
-        for (size_t j = 0; j < ents.size(); j++) ell[j * npad + i] = ents[j].code;
+        deg[i] = (int)ents.size();
+        for (size_t j = 0; j < ents.size(); j++) tile_ents[(size_t)i * md + j] = ents[j];
       }
       for (int i = 0; i < n; i++) lmap[P[i]] = -1;
       for (int j = 0; j < nh; j++) lmap[hpts[j]] = -1;
+
+      /* ---- placement.  A half-warp (16 lanes = 16 consecutive tile points) at step j of the face walk
+       * reads one normal and one var row per lane with 8-byte loads; two lanes collide when they read different
+       * words of the same bank pair.  Row r / slot s sits in bank-pair class r mod 16 / s mod 16 (row and slot
+       * strides are 7 and 3 words, both odd).  Own rows are fixed by the tile order; halo rows and face slots
+       * are free: greedily give each the class that adds the fewest collisions over the groups it is read in. */
+      slot_of.assign((size_t)nf, -1); hpos_of.assign((size_t)nh, -1);
+      const int nhw = (n + 15) / 16, ngrp = nhw * md;
+      if (!place_by_bank) {
+        for (int f = 0; f < nf; f++) slot_of[f] = f;
+        for (int h = 0; h < nh; h++) hpos_of[h] = h;
+      } else {
+        cntv.assign((size_t)ngrp * 16, 0); cntn.assign((size_t)ngrp * 16, 0);
+        /* own rows: distinct rows per group */
+        for (int hw = 0; hw < nhw; hw++)
+          for (int j = 0; j < md; j++) {
+            unsigned char *cv = &cntv[((size_t)hw * md + j) * 16];
+            int seen[16], ns = 0;
+            for (int l = 0; l < 16; l++) {
+              const int i = hw * 16 + l;
+              if (i >= n || j >= deg[i]) continue;
+              const int r = tile_ents[(size_t)i * md + j].nbr;
+              if (r >= n) continue;
+              bool dup = false;
+              for (int t = 0; t < ns; t++) if (seen[t] == r) dup = true;
+              if (!dup) { seen[ns++] = r; cv[r & 15]++; }
+            }
+          }
+        auto place = [&](int nobj, bool is_face, std::vector<unsigned char> &cnt, std::vector<int> &pos_of, int npos, int base_mod) {
+          /* object -> distinct groups */
+          grp_off.assign((size_t)nobj + 1, 0);
+          auto obj_of = [&](const Ent &e) { return is_face ? e.fid : (e.nbr >= n ? e.nbr - n : -1); };
+          for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1) { for (int o = 0; o < nobj; o++) grp_off[(size_t)o + 1] += grp_off[o]; grp_list.assign((size_t)grp_off[nobj], -1); }
+            std::vector<int> fill;
+            if (pass == 1) fill.assign(grp_off.begin(), grp_off.end() - 1);
+            for (int i = 0; i < n; i++)
+              for (int j = 0; j < deg[i]; j++) {
+                const int o = obj_of(tile_ents[(size_t)i * md + j]);
+                if (o < 0) continue;
+                const int gidx = (i / 16) * md + j;
+                if (pass == 0) grp_off[(size_t)o + 1]++;
+                else {
+                  bool dup = false;
+                  for (int t = grp_off[o]; t < fill[o]; t++) if (grp_list[t] == gidx) dup = true;
+                  if (!dup) grp_list[fill[o]++] = gidx;
+                }
+              }
+          }
+          const int cap = npos / 16;
+          int used[16] = {0};
+          for (int o = 0; o < nobj; o++) {
+            int best = -1, best_cost = 1 << 30;
+            for (int c0 = 0; c0 < 16; c0++) {
+              const int c = (c0 + o) & 15; /* rotate the tie-break so that classes fill evenly */
+              if (used[c] >= cap) continue;
+              int cost = 0;
+              for (int t = grp_off[o]; t < grp_off[(size_t)o + 1]; t++) {
+                const int gi = grp_list[t];
+                if (gi < 0) continue;
+                const unsigned char *cc = &cnt[(size_t)gi * 16];
+                int mx = 0;
+                for (int x = 0; x < 16; x++) mx = std::max(mx, (int)cc[x]);
+                if (cc[c] + 1 > mx) cost += 4;          /* raises this group's wavefront count */
+                cost += cc[c];                          /* prefer emptier classes */
+              }
+              if (cost < best_cost) { best_cost = cost; best = c; }
+            }
+            ASSERT(best >= 0);
+            for (int t = grp_off[o]; t < grp_off[(size_t)o + 1]; t++) if (grp_list[t] >= 0) cnt[(size_t)grp_list[t] * 16 + best]++;
+            /* position with (base_mod + pos) mod 16 == best */
+            const int first = ((best - base_mod) % 16 + 16) % 16;
+            pos_of[o] = first + 16 * used[best];
+            used[best]++;
+          }
+        };
+        place(nh, false, cntv, hpos_of, nhpos, n_even & 15);
+        place(nf, true, cntn, slot_of, nslots, 0);
+      }
+
+      /* ---- emit */
+      for (int f = 0; f < nf; f++) {
+        const int sl = slot_of[f], gf = fids[f];
+        ASSERT(sl >= 0 && sl < nslots);
+        nrm[3 * sl + 0] = sd->fnormal[gf][0]; nrm[3 * sl + 1] = sd->fnormal[gf][1]; nrm[3 * sl + 2] = sd->fnormal[gf][2];
+      }
+      for (int h = 0; h < nh; h++) { ASSERT(hpos_of[h] >= 0 && hpos_of[h] < nhpos); hrows[hpos_of[h]] = (uint32_t)out.row_of_point[hpts[h]]; }
+      for (int i = 0; i < n; i++)
+        for (int j = 0; j < deg[i]; j++) {
+          const Ent &e = tile_ents[(size_t)i * md + j];
+          const uint32_t loc = e.nbr < n ? (uint32_t)e.nbr : (uint32_t)(n_even + hpos_of[e.nbr - n]);
+          ell[(size_t)j * npad + i] = loc | ((uint32_t)slot_of[e.fid] << 16) | (e.sign << 31);
+        }
+
+      /* shared-memory wavefront estimate of the face walk: 7 var words + 3 normal words per face end */
+      for (int w0 = 0; w0 < n; w0 += 16)
+        for (int j = 0; j < md; j++) {
+          int cnt_v[16] = {0}, cnt_n[16] = {0}, nact = 0;
+          uint32_t seen_v[16], seen_n[16]; int nsv = 0, nsn = 0;
+          for (int l = 0; l < 16; l++) {
+            const int i = w0 + l;
+            if (i >= n) break;
+            const uint32_t e = ell[(size_t)j * npad + i];
+            if (e == CFDP_ADJ_PAD) continue;
+            nact++;
+            const uint32_t r = e & 0xFFFFu, sl = (e >> 16) & 0x7FFFu;
+            bool dup = false;
+            for (int t = 0; t < nsv; t++) if (seen_v[t] == r) dup = true;
+            if (!dup) { seen_v[nsv++] = r; cnt_v[r & 15]++; }
+            dup = false;
+            for (int t = 0; t < nsn; t++) if (seen_n[t] == sl) dup = true;
+            if (!dup) { seen_n[nsn++] = sl; cnt_n[sl & 15]++; }
+          }
+          if (!nact) continue;
+          int mv = 0, mn = 0;
+          for (int c = 0; c < 16; c++) { mv = std::max(mv, cnt_v[c]); mn = std::max(mn, cnt_n[c]); }
+          wf_min_total += 10; wf_est_total += 7 * mv + 3 * mn;
+        }
     }
   }
+  out.lds_wavefronts_min = wf_min_total; out.lds_wavefronts_est = wf_est_total;
 }

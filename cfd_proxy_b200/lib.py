@@ -84,7 +84,8 @@ class MeshDomain(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in (
         "nfaces", "nown", "nall", "rows", "ntiles", "nboundary_tiles", "tile_faces", "halo_refs",
-        "blob_bytes", "send_rows_local", "send_rows_remote", "alg_bytes", "h2d_bytes", "d2h_bytes", "launches")] + [
+        "blob_bytes", "send_rows_local", "send_rows_remote", "alg_bytes", "h2d_bytes", "d2h_bytes", "launches",
+        "lds_wavefronts_min", "lds_wavefronts_est")] + [
         ("last_kernel_ms", C.c_double),
         ("nprocs", C.c_int), ("proc_rank", C.c_int), ("ndomains_hosted", C.c_int),
         ("tile_points", C.c_int), ("smem_bytes", C.c_int),

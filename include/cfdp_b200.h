@@ -203,6 +203,7 @@ typedef struct {
   long long alg_bytes;       /* F*32 + P_all*56 + P_own*176 */
   long long h2d_bytes, d2h_bytes; /* per e2e step */
   long long launches;        /* kernels launched by this library so far */
+  long long lds_wavefronts_min, lds_wavefronts_est; /* schedule quality: shared-memory wavefronts of the face walk, conflict-free vs estimated */
   double last_kernel_ms;     /* mean device time of the gradient kernel(s) per iteration in the last cfdp_iterate */
   int nprocs, proc_rank, ndomains_hosted, tile_points, smem_bytes;
 } cfdp_stats;

@@ -49,7 +49,10 @@ CASES = [
 
 @pytest.mark.parametrize("n,p,order,hexfrac,tile,torder", CASES)
 @pytest.mark.parametrize("variant", ["comm_free", "mpi_bulk_sync", "mpi_early_recv", "mpi_async", "gaspi_async"])
-def test_exact_mode_bit_identical(session_factory, n, p, order, hexfrac, tile, torder, variant):
+@pytest.mark.parametrize("kernel", [2, 1])   # 2 = pipelined TMA kernel (production), 1 = one tile per CTA
+def test_exact_mode_bit_identical(session_factory, monkeypatch, n, p, order, hexfrac, tile, torder, variant, kernel):
+    monkeypatch.setenv("CFDP_KERNEL", str(kernel))
+    monkeypatch.setenv("CFDP_CHUNK", "3")
     spec = M.make_spec(n, p, order=order, brick=4, hexfrac=hexfrac)
     nd = p[0] * p[1] * p[2]
     doms = [M.gen_domain(spec, r) for r in range(nd)]
@@ -137,7 +140,8 @@ def test_var_update_between_calls(session_factory):
 
 
 def test_large_mesh_properties(session_factory):
-    """Full-size properties (no oracle run): linearity in var and exact reproducibility."""
+    """Full-size properties (no oracle run): linearity in var and exact reproducibility, and the two
+    independent kernels agree bit for bit."""
     spec = M.make_spec((128, 128, 96), (2, 2, 2), order="lex", hexfrac=0.3)
     S = session_factory(8, device=0)
     S.load_spec(spec)
@@ -156,3 +160,15 @@ def test_large_mesh_properties(session_factory):
     S.download_grad()
     for a, d in enumerate(S.domains):
         assert bits_differ(d.grad, 4.0 * g1[a]) == 0
+    import os
+    os.environ["CFDP_KERNEL"] = "1"
+    try:
+        S2 = session_factory(8, device=0)
+        S2.load_spec(spec)
+        S2.setup()
+        S2.iterate("mpi_async", 1)
+        S2.download_grad()
+        for a, d in enumerate(S2.domains):
+            assert bits_differ(d.grad, g1[a]) == 0
+    finally:
+        os.environ.pop("CFDP_KERNEL", None)

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Kernel-only sweep (comm_free iterations) over schedule / kernel configurations.
+usage: python tools/kbench.py [--mpoints 16] cfg ...   cfg = kernel:tile:chunk:fma:order[:stages:split]  e.g. 2:256:16:0:lex:2:2"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import cfd_proxy_b200.mesh as M
+from cfd_proxy_b200.driver import Session
+from bench import lattice_for, measured_peak
+
+def main():
+    args = sys.argv[1:]
+    mp = 16.0
+    if args and args[0] == "--mpoints":
+        mp = float(args[1]); args = args[2:]
+    n = lattice_for(mp)
+    peak, _ = measured_peak()
+    for cfg in args:
+        parts = cfg.split(":") + ["2", "2"]
+        k, tile, chunk, fma, order, stages, split = parts[:7]
+        os.environ["CFDP_KERNEL"] = k
+        os.environ["CFDP_CHUNK"] = chunk
+        os.environ["CFDP_STAGES"] = stages
+        os.environ["CFDP_SPLIT"] = split
+        t0 = time.time()
+        with Session(8, device=0, tile_points=int(tile), tile_order=1 if order == "brickid" else 0) as S:
+            spec = M.make_spec(n, (2, 2, 2), order="brick" if order.startswith("brick") else order, brick=8, jitter=0.1, allow_big=True)
+            S.load_spec(spec); S.setup()
+            S.lib.cfdp_set_exact(0 if fma == "1" else 1)
+            S.iterate("comm_free", 3)
+            ms = S.iterate("comm_free", 10) / 10
+            ms_a = S.iterate("mpi_async", 10) / 10
+            st = S.stats()
+            print(json.dumps(dict(cfg=cfg, kernel_ms=round(ms, 4), gfaces=round(st.nfaces / ms / 1e6, 2), frac=round(st.alg_bytes / ms / 1e6 / peak, 4),
+                                  async_ms=round(ms_a, 4), smem=st.smem_bytes, tiles=st.ntiles, dup=round(st.tile_faces / st.nfaces, 3),
+                                  blob_B_per_face=round(st.blob_bytes / st.nfaces, 2), setup_s=round(time.time() - t0, 1))), flush=True)
+
+if __name__ == "__main__":
+    main()

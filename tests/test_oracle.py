@@ -1,0 +1,99 @@
+"""Pins the oracle (oracle/gg_oracle.c + oracle/oracle.py) against the UNMODIFIED reference:
+  * the committed golden fixtures (tests/golden/*.npz, produced by tests/golden/make_golden.py from
+    oracle/_ref/ref_harness) -- runs everywhere, including the GPU box,
+  * a live run of oracle/_ref when it has been built in this tree (the container with /root/reference).
+The reference itself ships no golden vectors or numerical tests."""
+import numpy as np
+import pytest
+
+import cfd_proxy_b200.mesh as M
+from oracle import oracle as O
+from helpers import GOLDEN, bits_differ, golden_grad, golden_index, load_golden
+
+EPS = np.finfo(np.float64).eps
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_oracle_bit_identical_to_reference_one_thread(name):
+    z, spec, doms, lvl = load_golden(name)
+    nd = len(doms)
+    recv, send = O.recvsend_index(doms) if nd > 1 else ([{}], [{}])
+    grads = [O.gradients(d, M.var_for(d), is_send=O.is_send_mask(d, send[a]), order=1) for a, d in enumerate(doms)]
+    for a, d in enumerate(doms):
+        ref = golden_grad(z, "comm_free", 1, a)
+        assert bits_differ(ref[:d["nown"]], grads[a][:d["nown"]]) == 0
+        assert np.isnan(ref[d["nown"]:]).all()            # comm_free never touches ghost rows (harness pre-fills NaN)
+    if nd > 1:
+        ex = O.exchange(grads, recv, send)
+        for v in ("mpi_bulk_sync", "mpi_async"):
+            for a in range(nd):
+                assert bits_differ(golden_grad(z, v, 1, a), ex[a]) == 0      # own AND ghost rows
+        for a in range(nd):
+            gs, gr = golden_index(z, a, nd)
+            assert set(gs) == set(send[a]) and set(gr) == set(recv[a])
+            for k in gs:
+                assert np.array_equal(gs[k], send[a][k])                       # comm_data.c:197-222
+            for k in gr:
+                assert np.array_equal(gr[k], recv[a][k])                       # comm_data.c:163-174
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_oracle_within_tolerance_of_threaded_reference(name):
+    """With 3 OpenMP threads the reference sums in another order: SURVEY 8(c) tolerance."""
+    z, spec, doms, lvl = load_golden(name)
+    nd = len(doms)
+    recv, send = O.recvsend_index(doms) if nd > 1 else ([{}], [{}])
+    v = "mpi_async" if nd > 1 else "comm_free"
+    for a, d in enumerate(doms):
+        var = M.var_for(d)
+        g = O.gradients(d, var, is_send=O.is_send_mask(d, send[a]), order=1)
+        ref = golden_grad(z, v, 3, a)
+        scale = O.error_scale(d, var)[:, None, None]
+        err = np.abs(ref[:d["nown"]] - g[:d["nown"]])
+        assert (err <= 1e-12 * np.abs(g[:d["nown"]]) + 64 * EPS * scale).all()
+
+
+def test_numpy_restatement_agrees():
+    _, spec, doms, _ = load_golden("single")
+    d = doms[0]
+    var = M.var_for(d)
+    g1 = O.gradients(d, var, order=0)
+    g2 = O.gradients_numpy(d, var)
+    scale = O.error_scale(d, var)[:, None, None]
+    assert (np.abs(g1[:d["nown"]] - g2[:d["nown"]]) <= 64 * EPS * scale).all()
+
+
+def test_pack_unpack_roundtrip():
+    rng = np.random.default_rng(1)
+    data = rng.standard_normal((50, 21))
+    idx = rng.permutation(50)[:17].astype(np.int32)
+    import ctypes as C
+    buf = np.zeros((17, 21))
+    O.lib().oracle_pack(data.ctypes.data_as(C.POINTER(C.c_double)), 21, idx.ctypes.data_as(C.POINTER(C.c_int)), 17,
+                        buf.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.array_equal(buf, data[idx])
+    out = np.zeros_like(data)
+    O.lib().oracle_unpack(out.ctypes.data_as(C.POINTER(C.c_double)), 21, idx.ctypes.data_as(C.POINTER(C.c_int)), 17,
+                          buf.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.array_equal(out[idx], data[idx])
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("threads", [1, 4])
+def test_live_reference_run(tmp_path, threads):
+    spec = M.f6like_spec(12, lvl=4)
+    prefix = str(tmp_path / "dualgrid")
+    doms = M.write_mesh(prefix, spec, lvl=4)
+    recv, send = O.recvsend_index(doms)
+    ref = O.run_ref(prefix, 4, 12, "mpi_async", 2, str(tmp_path / "out"), threads=threads)
+    grads = [O.gradients(d, M.var_for(d), is_send=O.is_send_mask(d, send[a]), order=1) for a, d in enumerate(doms)]
+    grads = O.exchange(grads, recv, send)
+    for a, d in enumerate(doms):
+        if threads == 1:
+            assert bits_differ(ref[a]["grad"], grads[a]) == 0
+        else:
+            scale = O.error_scale(d, M.var_for(d))[:, None, None]
+            err = np.abs(ref[a]["grad"][:d["nown"]] - grads[a][:d["nown"]])
+            assert (err <= 1e-12 * np.abs(grads[a][:d["nown"]]) + 64 * EPS * scale).all()
+        for k in send[a]:
+            assert np.array_equal(ref[a]["sendindex"][k], send[a][k])

@@ -224,6 +224,10 @@ def main():
     faces_total = allsum(float(st.nfaces))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # clocks are sampled from before the kernel-only section to the end of the timed region
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # ---- kernel-only (comm_free) iterations: the roofline number -------------------------------
     S.iterate("comm_free", max(args.warmup, 3))
     barrier()
@@ -243,15 +247,18 @@ def main():
     # ---- timed region: K iterations of grad + halo ---------------------------------------------
     S.iterate(args.variant, max(args.warmup, 3))
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = S.stats().launches
     ms = S.iterate(args.variant, args.steps)
     barrier()
     launches = S.stats().launches - l0
     ms = allmax(ms)
+    if rank == 0 and ms < 400:     # keep the GPU under the same load until the sampler has a few readings
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            S.iterate("comm_free", args.steps)      # no communication: the other ranks are not involved
     clocks = sampler.stop() if rank == 0 else {}
+    if world > 1:
+        dist.barrier()
     value = faces_total * args.steps / (ms * 1e-3)
 
     # ---- end to end through the drop-in call with host buffers -----------------------------------
@@ -292,7 +299,7 @@ def main():
                         setup_s=round(t_setup, 1), tiles=int(st.ntiles), boundary_tiles=int(st.nboundary_tiles),
                         halo_rows_on_device=int(st.send_rows_local), halo_rows_over_nvlink=int(st.send_rows_remote)),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                          kernel="gg_tile_kernel", kernel_ms=ms_k, alg_bytes_per_launch=int(alg),
+                          kernel="gg_tile_pipe_kernel" if int(os.environ.get("CFDP_KERNEL", "2")) == 2 else "gg_tile_kernel", kernel_ms=ms_k, alg_bytes_per_launch=int(alg),
                           alg_bytes_per_face=alg / float(st.nfaces), peak_source=peak_src,
                           frac_of_8TBps_nominal=achieved / 8000.0, kernel_faces_per_s=float(st.nfaces) / (ms_k * 1e-3)),
             cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)

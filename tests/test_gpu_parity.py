@@ -209,3 +209,30 @@ def test_cuda_path_matches_reference_golden_vectors(session_factory, tmp_path, n
         ref3 = golden_grad(z, v, 3, a)
         ok, mx = within_tolerance(d.grad, ref3, doms[a], M.var_for(doms[a]))
         assert ok, mx
+
+
+def test_reference_main_runs_on_the_library(tmp_path):
+    """oracle/_ref/hybrid.f6.b200.exe = the reference's UNMODIFIED src/hybrid.f6.c linked against
+    libcfdp_b200.so (built by `make -C oracle dropin` where /root/reference exists): the drop-in boundary
+    carries the reference's own main() to '*** SUCCESS', and the gradients it leaves in sd->grad match the oracle."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(O.HERE), "oracle", "_ref", "hybrid.f6.b200.exe")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/hybrid.f6.b200.exe not built")
+    spec = M.make_spec((24, 20, 16), (1, 1, 1), hexfrac=0.3)
+    prefix = str(tmp_path / "dualgrid")
+    doms = M.write_mesh(prefix, spec, lvl=1, with_var=False)
+    r = subprocess.run([exe, "-lvl", "1", "dualgrid"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "*** SUCCESS" in r.stdout and "*** TIMINGS" in r.stdout and "comm_free:" in r.stdout
+    # var == 1.0 (init_solver_data, solver_data.c:26-36): checksum of the oracle's gradients on the same mesh
+    d = doms[0]
+    g = O.gradients(d, np.ones((d["nall"], 7)), order=1)
+    line = [l for l in r.stdout.splitlines() if "CHECKSUM" in l][0]
+    got = float(line.split(":")[1])
+    want = 0.0
+    for v in g[:d["nown"]].ravel():
+        want += v
+    assert got == want

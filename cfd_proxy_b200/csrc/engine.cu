@@ -108,7 +108,7 @@ struct Engine {
   TileDesc *d_tiles = nullptr;
   size_t blob_bytes = 0;
   int smem_bytes = 0, region0_doubles = 0, block_threads = 0;
-  int kernel_version = 2, chunk = 16, smem_v1 = 0, split = 2; ggk::PipeLayout pipe = {0, 2, 256}; uint32_t max_footprint = 0;
+  int kernel_version = 2, chunk = 16, smem_v1 = 0; ggk::PipeLayout pipe = {0, 256, nullptr}; uint32_t max_footprint = 0;
   size_t max_blob = 0; int max_nhalo = 0;
   std::vector<int *> d_rowmap;     /* per hosted domain: [nall] global device row of host point */
   double *d_stage = nullptr; size_t stage_bytes = 0;
@@ -214,7 +214,7 @@ extern "C" int cfdp_configure(int proc_rank, int nprocs, int ndomains_total, int
   E.sopt.order = env_int("CFDP_TILE_ORDER", 0);
   E.sopt.sort_in_tile = env_int("CFDP_SORT_IN_TILE", 1);
   E.sopt.bank_placement = env_int("CFDP_BANK_PLACEMENT", 1);
-  E.sopt.stage_budget = env_int("CFDP_STAGE_BUDGET", 110 * 1024); /* two tiles (two CTAs or two stages) in 228 KB of shared memory per SM */
+  E.sopt.stage_budget = env_int("CFDP_STAGE_BUDGET", 105 * 1024); /* two tiles (two CTAs or two stages) in 228 KB of shared memory per SM */
   E.exact = env_int("CFDP_EXACT", 1);
   E.configured = true;
   return 0;
@@ -361,12 +361,10 @@ static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st)
   if (ntiles <= 0) return;
   if (E.kernel_version == 2) {
     const unsigned grid = (unsigned)((ntiles + E.chunk - 1) / E.chunk);
-    const int thr = E.block_threads * E.split;
-#define PIPE_LAUNCH(EX, SP, MB) ggk::gg_tile_pipe_kernel<EX, SP, MB><<<grid, thr, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.chunk, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.pipe)
-    if (E.split == 2) { if (E.exact) PIPE_LAUNCH(true, 2, 1); else PIPE_LAUNCH(false, 2, 1); }
-    else if (E.pipe.stages == 2) { if (E.exact) PIPE_LAUNCH(true, 1, 1); else PIPE_LAUNCH(false, 1, 1); }
-    else { if (E.exact) PIPE_LAUNCH(true, 1, 2); else PIPE_LAUNCH(false, 1, 2); }
-#undef PIPE_LAUNCH
+    if (E.exact)
+      ggk::gg_tile_pipe_kernel<true><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.chunk, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.pipe);
+    else
+      ggk::gg_tile_pipe_kernel<false><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.chunk, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.pipe);
   } else {
     if (E.exact)
       ggk::gg_tile_kernel<true><<<(unsigned)ntiles, E.block_threads, E.smem_v1, st>>>(E.d_tiles + tile0, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.region0_doubles);
@@ -535,8 +533,9 @@ extern "C" void cfdp_commit(void)
     CUDA_CHECK(cudaMemcpy(E.d_pvol, pv.data(), pv.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
 
-  E.block_threads = (int)std::max(align_up((size_t)E.max_npts, 32), align_up(((size_t)E.max_nhalo + CFDP_HALO_PER_THREAD - 1) / CFDP_HALO_PER_THREAD, 32));
+  E.block_threads = (int)align_up((size_t)E.max_npts, 32);
   ASSERT(E.block_threads <= CFDP_MAX_TILE_POINTS);
+  ASSERT(E.max_nhalo <= CFDP_MAX_HALO_POS);
   /* v1 (one tile per CTA) */
   E.region0_doubles = (int)align_up((size_t)std::max(E.max_nfaces * 3, E.max_npts * CFDP_DIM2), 2);
   E.smem_v1 = (int)((size_t)E.region0_doubles * 8 + align_up((size_t)E.max_nloc * NGRAD * 8, 16));
@@ -544,28 +543,21 @@ extern "C" void cfdp_commit(void)
   E.pipe.stage_bytes = E.max_footprint;
   E.kernel_version = env_int("CFDP_KERNEL", 2);
   E.chunk = std::min(CFDP_MAX_CHUNK, std::max(1, env_int("CFDP_CHUNK", 16)));
-  E.split = env_int("CFDP_SPLIT", 1) == 2 ? 2 : 1;
-  E.pipe.stages = env_int("CFDP_STAGES", 1) == 2 ? 2 : 1;
   E.pipe.block_points = E.block_threads;
-  if (E.pipe.stages == 1) E.split = 1; /* single-stage relies on two resident CTAs: 128 registers per thread at most */
+  if (env_int("CFDP_PHASE_PROF", 0)) { CUDA_CHECK(cudaMalloc(&E.pipe.prof, 8 * sizeof(unsigned long long))); CUDA_CHECK(cudaMemset(E.pipe.prof, 0, 8 * sizeof(unsigned long long))); }
   const int smem_limit = 227 * 1024 - 256;
-  if (E.kernel_version == 2 && E.pipe.stages == 2 && 2 * (int)E.pipe.stage_bytes > smem_limit) E.pipe.stages = 1;
   if (E.kernel_version == 2 && (int)E.pipe.stage_bytes > smem_limit) {
     fprintf(stderr, "cfdp: pipelined kernel needs %u B of shared memory per stage, falling back to the one-tile-per-CTA kernel "
                     "(lower CFDP_TILE_POINTS to avoid this)\n", E.pipe.stage_bytes);
     E.kernel_version = 1;
   }
   ASSERT(E.smem_v1 <= smem_limit);
-  E.smem_bytes = E.kernel_version == 2 ? E.pipe.stages * (int)E.pipe.stage_bytes : E.smem_v1;
+  E.smem_bytes = E.kernel_version == 2 ? (int)E.pipe.stage_bytes : E.smem_v1;
   CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
   CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
   if (E.kernel_version == 2) {
-    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
-    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
-    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
-    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
-    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
-    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
   }
 
   E.d_loc_dst = upload(E.h_loc_dst); E.d_loc_src = upload(E.h_loc_src);
@@ -688,6 +680,17 @@ extern "C" double cfdp_step_e2e(int variant)
   float ms = 0;
   CUDA_CHECK(cudaEventElapsedTime(&ms, E.ev_t0, E.ev_t1));
   return (double)ms;
+}
+
+/* debug: per-phase SM cycles of thread 0, summed over tiles (CFDP_PHASE_PROF=1) */
+extern "C" int cfdp_get_phase_profile(unsigned long long *out8, int reset)
+{
+  Engine &E = g_eng;
+  if (!E.pipe.prof) return -1;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  CUDA_CHECK(cudaMemcpy(out8, E.pipe.prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) CUDA_CHECK(cudaMemset(E.pipe.prof, 0, 8 * sizeof(unsigned long long)));
+  return 0;
 }
 
 extern "C" void cfdp_device_synchronize(void)
@@ -871,6 +874,7 @@ extern "C" void cfdp_finalize(void)
     delete d;
   }
   E.doms.clear(); E.d_rowmap.clear(); E.point_of_row.clear(); E.peers.clear(); E.send_rows_of.clear(); E.recv_rows_of.clear();
+  if (E.pipe.prof) { cudaFree(E.pipe.prof); E.pipe.prof = nullptr; }
   E.d_var = E.d_grad = E.d_pvol = nullptr; E.d_blob = nullptr; E.d_tiles = nullptr; E.d_stage = nullptr;
   E.d_loc_dst = E.d_loc_src = E.d_send_rows = E.d_recv_rows = nullptr; E.d_sendbuf = E.d_recvbuf = nullptr;
   E.committed = false; E.planned = false; E.configured = false;

@@ -30,7 +30,7 @@
 #include <stdint.h>
 #include "common.h"
 
-#define CFDP_HALO_PER_THREAD 8 /* halo rows a thread can gather per tile: nhalo <= 8 * blockDim */
+#define CFDP_MAX_HALO_POS 1024  /* halo positions of a tile (shared-memory index list of the prefetcher) */
 #define CFDP_MAX_CHUNK 64      /* tiles per CTA */
 
 namespace ggk {
@@ -68,6 +68,12 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src)
 {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
 {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -139,141 +145,162 @@ __host__ __device__ __forceinline__ uint32_t tile_footprint(uint32_t blob_bytes,
 }
 struct PipeLayout {
   uint32_t stage_bytes;
-  int stages;        /* 1: one buffer, latency hidden by a second resident CTA; 2: double buffered inside the CTA */
-  int block_points;  /* threads per equation group (multiple of 32, >= largest tile) */
+  int block_points;  /* threads per CTA (multiple of 32, >= largest tile) */
+  unsigned long long *prof; /* optional: SM cycles of thread 0 summed over tiles: [0] wait for data, [1] face walk, [2] rest of the tile, [4] tiles */
 };
 
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 /*
- * SPLIT = 1: one thread per point, 21 sums in registers.
- * SPLIT = 2: two threads per point (equations 0-3 and 4-6, warp-uniform roles): twice the warps for
- *            latency hiding at half the registers; normals / adjacency are read by both.
- * MINB     : resident CTAs per SM the register allocation must allow (2 with single-stage staging).
+ * Two CTAs per SM, each owning one shared-memory stage and a chunk of consecutive tiles.  Timeline of a tile t:
+ *   wait(mbarrier)            all of tile t has landed (bulk copies + halo gather)
+ *   face walk                 one thread per point, 21 sums in registers
+ *   S1 barrier                normals / adjacency / var of tile t are dead
+ *   early fetch of tile t+1   var rows, volumes, blob tail (bulk copies) and the halo gather (8-byte cp.async): everything
+ *                             that does not overlap the output staging of tile t
+ *   stage the rows of tile t  into the head of the stage (transposed through shared memory)
+ *   S2 barrier
+ *   TMA bulk store of the rows (one instruction), wait until shared memory has been read, then the head of tile
+ *   t+1's blob.  While this CTA waits, the other CTA of the SM computes.
+ * No thread ever blocks on a global load: HBM is touched only by asynchronous copies.
  */
-template <bool EXACT, int SPLIT, int MINB>
-__global__ void __launch_bounds__(CFDP_MAX_TILE_POINTS * SPLIT, MINB)
+template <bool EXACT>
+__global__ void __launch_bounds__(CFDP_MAX_TILE_POINTS, 2)
 gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, const unsigned char *__restrict__ blob,
                     const double *__restrict__ hvar, const double *__restrict__ pvol, double *__restrict__ grad, PipeLayout L)
 {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t full[2];
+  __shared__ uint64_t full;
   __shared__ TileDesc s_tds[CFDP_MAX_CHUNK];   /* descriptors of this CTA's tiles */
+  __shared__ __align__(16) uint32_t s_hidx[CFDP_MAX_HALO_POS]; /* halo row list of the tile being prefetched */
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int t_begin = blockIdx.x * chunk;
   const int t_end = min(t_begin + chunk, ntiles);
   if (t_begin >= t_end) return;
-  const int nst = L.stages;
   {
     const int nw = (t_end - t_begin) * (int)(sizeof(TileDesc) / 4);
     const uint32_t *g = reinterpret_cast<const uint32_t *>(tiles + t_begin);
     uint32_t *d = reinterpret_cast<uint32_t *>(s_tds);
     for (int i = tid; i < nw; i += nthr) d[i] = __ldg(g + i);
   }
-
   if (tid == 0) {
-    mbar_init(&full[0], (uint32_t)nthr + 1);
-    mbar_init(&full[1], (uint32_t)nthr + 1);
+    mbar_init(&full, (uint32_t)nthr + 1);
     fence_mbar_init();
   }
+  unsigned char *const st = smem;
 
-  /* prefetch state of this thread: descriptor and halo rows of the tile to be fetched next */
-  TileDesc pf_td;
-  uint32_t pf_h[CFDP_HALO_PER_THREAD];
-  auto load_pf_meta = [&](int t) {
+  /* halo row list of tile t (part of its blob) -> s_hidx, asynchronously */
+  auto stage_pf_index = [&](int t) {
     if (t < t_end) {
-      pf_td = s_tds[t - t_begin];
-      const uint32_t *hr = reinterpret_cast<const uint32_t *>(blob + pf_td.blob + pf_td.halo_off);
-#pragma unroll
-      for (int k = 0; k < CFDP_HALO_PER_THREAD; k++) {
-        const int i = tid + k * nthr;
-        pf_h[k] = i < (int)pf_td.nhalo ? __ldg(hr + i) : 0xFFFFFFFFu;
-      }
+      const TileDesc pd = s_tds[t - t_begin];
+      const uint4 *g = reinterpret_cast<const uint4 *>(blob + pd.blob + pd.halo_off);
+      const int n16 = (int)pd.nhalo >> 2; /* nhalo (positions) is a multiple of 16 */
+      for (int i = tid; i < n16; i += nthr) cp_async16(&s_hidx[4 * i], g + i);
+    }
+    cp_async_commit();
+  };
+  /* thread 0: announce the bytes of tile t and start its bulk copies for blob bytes [lo, hi) (+ var rows and volumes) */
+  auto bulk_part = [&](const TileDesc &pd, uint32_t lo, uint32_t hi, bool with_var, bool announce) {
+    const uint32_t n_even = CFDP_HALO_BASE((uint32_t)pd.npts);
+    const uint32_t nv = n_even * (NGRAD * 8), np = n_even * 8;
+    if (announce) mbar_arrive_expect_tx(&full, pd.blob_bytes + nv + np);
+    if (hi > lo) bulk_g2s(st + lo, blob + pd.blob + lo, hi - lo, &full);
+    if (with_var) {
+      bulk_g2s(st + tile_var_off(pd.blob_bytes, pd.npts), hvar + (size_t)pd.row0 * NGRAD, nv, &full);
+      bulk_g2s(st + tile_pvol_off(pd.blob_bytes, pd.npts, pd.nhalo), pvol + pd.row0, np, &full);
     }
   };
-  auto issue_pf = [&](int t, int s) {
-    if (t < t_end) {
-      unsigned char *st = smem + (size_t)s * L.stage_bytes;
-      const uint32_t n_even = CFDP_HALO_BASE((uint32_t)pf_td.npts);
-      const uint32_t voff = tile_var_off(pf_td.blob_bytes, pf_td.npts);
-      if (tid == 0) {
-        const uint32_t nb = pf_td.blob_bytes, nv = n_even * (NGRAD * 8), np = n_even * 8;
-        mbar_arrive_expect_tx(&full[s], nb + nv + np);
-        bulk_g2s(st, blob + pf_td.blob, nb, &full[s]);
-        bulk_g2s(st + voff, hvar + (size_t)pf_td.row0 * NGRAD, nv, &full[s]);
-        bulk_g2s(st + tile_pvol_off(pf_td.blob_bytes, pf_td.npts, pf_td.nhalo), pvol + pf_td.row0, np, &full[s]);
-      }
-      double *vs = reinterpret_cast<double *>(st + voff) + (size_t)n_even * NGRAD;
-#pragma unroll
-      for (int k = 0; k < CFDP_HALO_PER_THREAD; k++) {
-        if (pf_h[k] != 0xFFFFFFFFu) {
-          const double *src = hvar + (size_t)pf_h[k] * NGRAD;
-          double *dst = vs + (size_t)(tid + k * nthr) * NGRAD;
-#pragma unroll
-          for (int c = 0; c < NGRAD; c++) cp_async8(dst + c, src + c);
-        }
-      }
-      cp_async_mbar_arrive_noinc(&full[s]);
+  /* all threads: hvar rows of the halo points, consecutive lanes = consecutive words of a row */
+  auto gather_halo = [&](const TileDesc &pd) {
+    double *vs = reinterpret_cast<double *>(st + tile_var_off(pd.blob_bytes, pd.npts)) + (size_t)CFDP_HALO_BASE((uint32_t)pd.npts) * NGRAD;
+    const int nw = (int)pd.nhalo * NGRAD;
+    for (int i = tid; i < nw; i += nthr) {
+      const int r = i / NGRAD;
+      const uint32_t row = s_hidx[r];
+      if (row != 0xFFFFFFFFu) cp_async8(vs + i, hvar + (size_t)row * NGRAD + (i - r * NGRAD));
     }
+    cp_async_mbar_arrive_noinc(&full);
   };
 
-  __syncthreads(); /* descriptors and mbarriers visible */
-  load_pf_meta(t_begin);
-  issue_pf(t_begin, 0);
-  if (nst == 2) { load_pf_meta(t_begin + 1); issue_pf(t_begin + 1, 1); }
-
-  const int grp = tid / L.block_points;         /* warp-uniform: block_points is a multiple of 32 */
-  const int p = tid - grp * L.block_points;
+  __syncthreads(); /* descriptors and mbarrier visible */
+  stage_pf_index(t_begin);
+  cp_async_wait_all();
+  __syncthreads();
+  {
+    const TileDesc pd = s_tds[0];
+    if (tid == 0) bulk_part(pd, 0, pd.blob_bytes, true, true);
+    gather_halo(pd);
+  }
+  __syncthreads(); /* s_hidx may be refilled */
 
   for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
-    const int s = nst == 2 ? (it & 1) : 0;
-    const uint32_t parity = (uint32_t)(nst == 2 ? (it >> 1) : it) & 1u;
-    load_pf_meta(t + nst); /* consumed when this tile retires: latency hidden behind the face walk */
-    unsigned char *st = smem + (size_t)s * L.stage_bytes;
+    const bool has_next = t + 1 < t_end;
+    stage_pf_index(t + 1); /* lands during the face walk */
     const TileDesc td = s_tds[t - t_begin];
     const int npts = td.npts, nhalo = td.nhalo;
     double *s_nrm = reinterpret_cast<double *>(st);
     const double *s_hvar = reinterpret_cast<const double *>(st + tile_var_off(td.blob_bytes, td.npts));
     const double *s_pvol = reinterpret_cast<const double *>(st + tile_pvol_off(td.blob_bytes, td.npts, td.nhalo));
-    mbar_wait(&full[s], parity);
     const uint32_t *ell0 = reinterpret_cast<const uint32_t *>(st + td.halo_off + ((nhalo * 4 + 15) & ~15));
+    long long c0 = 0, c1 = 0, c2 = 0;
+    if (L.prof && tid == 0) c0 = clock64();
+    mbar_wait(&full, (uint32_t)it & 1u);
+    if (L.prof && tid == 0) c1 = clock64();
 
-    double acc[(SPLIT == 1 ? NGRAD : 4) * 3];
-    const bool active = p < npts;
+    double acc[NGRAD * 3];
+    const bool active = tid < npts;
     if (active) {
-      const double inv_vol = __ddiv_rn(1.0, s_pvol[p]);                 /* gradients.c:138 */
-      if (SPLIT == 1) {
-        point_rows<EXACT, 0, NGRAD>(p, ell0, td.npad, td.maxdeg, s_nrm, s_hvar, inv_vol, reinterpret_cast<double(&)[NGRAD * 3]>(acc));
-      } else if (grp == 0) {
-        point_rows<EXACT, 0, 4>(p, ell0, td.npad, td.maxdeg, s_nrm, s_hvar, inv_vol, reinterpret_cast<double(&)[12]>(acc));
-      } else {
-        point_rows<EXACT, 4, 3>(p, ell0, td.npad, td.maxdeg, s_nrm, s_hvar, inv_vol, reinterpret_cast<double(&)[9]>(acc));
+      const double inv_vol = __ddiv_rn(1.0, s_pvol[tid]);                 /* gradients.c:138 */
+      point_rows<EXACT, 0, NGRAD>(tid, ell0, td.npad, td.maxdeg, s_nrm, s_hvar, inv_vol, acc);
+    }
+    cp_async_wait_all(); /* this thread's share of the next halo row list is in s_hidx */
+    __syncthreads();     /* S1: normals, adjacency and var of this tile are dead */
+    if (L.prof && tid == 0) c2 = clock64();
+
+    /* the output rows are staged in [0, out_end); whatever of the next tile lives beyond can be fetched now */
+    const uint32_t out_rows = CFDP_HALO_BASE((uint32_t)npts);
+    const uint32_t out_end = (out_rows * (NGRAD * 3 * 8) + 127u) & ~127u;
+    TileDesc nd = td;
+    bool early = false;
+    if (has_next) {
+      nd = s_tds[t + 1 - t_begin];
+      early = tile_var_off(nd.blob_bytes, nd.npts) >= out_end;
+      if (early) {
+        if (tid == 0) bulk_part(nd, out_end < nd.blob_bytes ? out_end : nd.blob_bytes, nd.blob_bytes, true, true);
+        gather_halo(nd);
       }
     }
-    __syncthreads(); /* normals and adjacency are dead: the blob region becomes the output staging */
     if (active) {
-      double *o = s_nrm + p * (NGRAD * 3);
-      if (SPLIT == 1) {
+      double *o = s_nrm + tid * (NGRAD * 3);
 #pragma unroll
-        for (int k = 0; k < NGRAD * 3; k++) o[k] = acc[k];
-      } else if (grp == 0) {
-#pragma unroll
-        for (int k = 0; k < 12; k++) o[k] = acc[k];
-      } else {
-#pragma unroll
-        for (int k = 0; k < 9; k++) o[12 + k] = acc[k];
+      for (int k = 0; k < NGRAD * 3; k++) o[k] = acc[k];
+    }
+    fence_proxy_async(); /* the staged rows (generic proxy) become visible to the bulk store (async proxy) */
+    __syncthreads();     /* S2 */
+    if (tid == 0) {
+      bulk_s2g(grad + (size_t)td.row0 * (NGRAD * 3), s_nrm, out_rows * (NGRAD * 3 * 8)); /* rows beyond npts are alignment padding */
+      bulk_commit();
+      bulk_wait_read(); /* shared memory may be overwritten */
+      if (has_next) {
+        if (early) bulk_part(nd, 0, out_end < nd.blob_bytes ? out_end : nd.blob_bytes, false, false);
+        else bulk_part(nd, 0, nd.blob_bytes, true, true);
       }
     }
-    __syncthreads();
-    {
-      double *gout = grad + (size_t)td.row0 * (NGRAD * 3);
-      const int n = npts * NGRAD * 3, n2 = n >> 1;
-      double2 *g2 = reinterpret_cast<double2 *>(gout);
-      const double2 *s2 = reinterpret_cast<const double2 *>(s_nrm);
-      for (int i = tid; i < n2; i += nthr) g2[i] = s2[i];
-      if ((n & 1) && tid == 0) gout[n - 1] = s_nrm[n - 1];
+    if (has_next && !early) { /* rare (a much smaller tile follows): its var rows overlap the staged rows */
+      __syncthreads();
+      gather_halo(nd);
+      __syncthreads();
     }
-    fence_proxy_async(); /* generic-proxy accesses of this stage are ordered before the next bulk copy into it */
-    __syncthreads();
-    issue_pf(t + nst, s);
+    if (L.prof && tid == 0) {
+      const long long c3 = clock64();
+      atomicAdd(L.prof + 0, (unsigned long long)(c1 - c0)); atomicAdd(L.prof + 1, (unsigned long long)(c2 - c1));
+      atomicAdd(L.prof + 2, (unsigned long long)(c3 - c2)); atomicAdd(L.prof + 4, 1ull);
+    }
   }
 }
 

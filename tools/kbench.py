@@ -30,6 +30,17 @@ def main():
             ms = S.iterate("comm_free", 10) / 10
             ms_a = S.iterate("mpi_async", 10) / 10
             st = S.stats()
+            prof = None
+            if os.environ.get("CFDP_PHASE_PROF"):
+                import ctypes as C
+                buf = (C.c_ulonglong * 8)()
+                S.lib.cfdp_get_phase_profile.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+                S.lib.cfdp_get_phase_profile(buf, 1)
+                S.iterate("comm_free", 5)
+                S.lib.cfdp_get_phase_profile(buf, 1)
+                nt = max(buf[4], 1)
+                prof = dict(wait=round(buf[0] / nt), walk=round(buf[1] / nt), rest=round(buf[2] / nt))
+                print("  phase cycles per tile (thread 0):", prof, flush=True)
             print(json.dumps(dict(cfg=cfg, kernel_ms=round(ms, 4), gfaces=round(st.nfaces / ms / 1e6, 2), frac=round(st.alg_bytes / ms / 1e6 / peak, 4),
                                   async_ms=round(ms_a, 4), smem=st.smem_bytes, tiles=st.ntiles, dup=round(st.tile_faces / st.nfaces, 3),
                                   blob_B_per_face=round(st.blob_bytes / st.nfaces, 2), setup_s=round(time.time() - t0, 1))), flush=True)

@@ -244,6 +244,11 @@ def main():
     except Exception:
         pass
 
+    # ---- how much of the exchange is hidden: bulk-synchronous (compute, then exchange) vs overlapped ----
+    S.iterate("mpi_bulk_sync", max(args.warmup, 3))
+    barrier()
+    ms_bulk = allmax(S.iterate("mpi_bulk_sync", args.steps) / args.steps)
+
     # ---- timed region: K iterations of grad + halo ---------------------------------------------
     S.iterate(args.variant, max(args.warmup, 3))
     barrier()
@@ -302,6 +307,11 @@ def main():
                           kernel="gg_tile_pipe_kernel" if int(os.environ.get("CFDP_KERNEL", "2")) == 2 else "gg_tile_kernel", kernel_ms=ms_k, alg_bytes_per_launch=int(alg),
                           alg_bytes_per_face=alg / float(st.nfaces), peak_source=peak_src,
                           frac_of_8TBps_nominal=achieved / 8000.0, kernel_faces_per_s=float(st.nfaces) / (ms_k * 1e-3)),
+            halo=dict(ms_comm_free=ms_k, ms_bulk_sync=ms_bulk, ms_overlapped=ms / args.steps,
+                      exchange_ms=max(ms_bulk - ms_k, 0.0),
+                      hidden_frac=(1.0 - max(ms / args.steps - ms_k, 0.0) / (ms_bulk - ms_k)) if ms_bulk > ms_k * 1.0005 else None,
+                      nvlink_bytes_per_iteration_per_gpu=int(st.send_rows_remote) * 168,
+                      note="hidden_frac = 1 - (t_overlapped - t_comm_free) / (t_bulk_sync - t_comm_free), variant timed: " + args.variant),
             cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line))
     S.close()

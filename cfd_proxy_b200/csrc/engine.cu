@@ -20,6 +20,7 @@
  *   tiles           TileDesc list: boundary tiles of all domains, then interior tiles of all domains
  */
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <dlfcn.h>
 #include <string.h>
 #include <unistd.h>
@@ -108,7 +109,8 @@ struct Engine {
   TileDesc *d_tiles = nullptr;
   size_t blob_bytes = 0;
   int smem_bytes = 0, region0_doubles = 0, block_threads = 0;
-  int kernel_version = 2, chunk = 16, smem_v1 = 0; ggk::PipeLayout pipe = {0, 256, nullptr}; uint32_t max_footprint = 0;
+  int kernel_version = 2, chunk = 16, smem_v1 = 0; ggk::PipeLayout pipe = {0, 256, nullptr, nullptr, 0};
+  unsigned long long *d_progress = nullptr; unsigned long long progress_target = 0; int fused_signal = 1; uint32_t max_footprint = 0;
   size_t max_blob = 0; int max_nhalo = 0;
   std::vector<int *> d_rowmap;     /* per hosted domain: [nall] global device row of host point */
   double *d_stage = nullptr; size_t stage_bytes = 0;
@@ -128,6 +130,7 @@ struct Engine {
   std::vector<std::vector<int>> point_of_row; /* per hosted domain: domain-relative row -> host point (-1 padding) */
   cudaStream_t s_comp = nullptr, s_comm = nullptr;
   cudaEvent_t ev_b = nullptr, ev_x = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t timeline_ek = nullptr, timeline_ex = nullptr;
   nccl_comm comm = nullptr;
   /* stats */
   long long launches = 0;
@@ -168,8 +171,11 @@ static void ensure_device(void)
   }
   ASSERT(E.device < n);
   CUDA_CHECK(cudaSetDevice(E.device));
-  CUDA_CHECK(cudaStreamCreateWithFlags(&E.s_comp, cudaStreamNonBlocking));
-  CUDA_CHECK(cudaStreamCreateWithFlags(&E.s_comm, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CUDA_CHECK(cudaStreamCreateWithPriority(&E.s_comp, cudaStreamNonBlocking, prio_lo));
+  /* the exchange kernels (pack, NCCL, unpack) must get the SM slots the gradient grid frees: highest priority */
+  CUDA_CHECK(cudaStreamCreateWithPriority(&E.s_comm, cudaStreamNonBlocking, prio_hi));
   CUDA_CHECK(cudaEventCreateWithFlags(&E.ev_b, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&E.ev_x, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreate(&E.ev_t0));
@@ -349,16 +355,18 @@ static void launch_rows_copy(double *dst, const uint32_t *dst_rows, const double
   if (nrows <= 0) return;
   const long long total = nrows * width;
   long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  static const long long cap = env_int("CFDP_COPY_BLOCKS", 148 * 16);
+  if (blocks > cap) blocks = cap;
   rows_copy_kernel<<<(unsigned)blocks, 256, 0, st>>>(dst, dst_rows, src, src_rows, nrows, width, scale);
   CUDA_CHECK(cudaGetLastError());
   g_eng.launches++;
 }
 
-static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st)
+static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st, int nsignal = 0)
 {
   Engine &E = g_eng;
   if (ntiles <= 0) return;
+  E.pipe.nsignal = nsignal; E.pipe.progress = E.d_progress;
   if (E.kernel_version == 2) {
     const unsigned grid = (unsigned)((ntiles + E.chunk - 1) / E.chunk);
     if (E.exact)
@@ -542,8 +550,10 @@ extern "C" void cfdp_commit(void)
   /* v2 (pipelined): two stages of [blob | var rows | volumes] */
   E.pipe.stage_bytes = E.max_footprint;
   E.kernel_version = env_int("CFDP_KERNEL", 2);
-  E.chunk = std::min(CFDP_MAX_CHUNK, std::max(1, env_int("CFDP_CHUNK", 16)));
+  E.chunk = std::min(CFDP_MAX_CHUNK, std::max(1, env_int("CFDP_CHUNK", 8)));
   E.pipe.block_points = E.block_threads;
+  E.fused_signal = env_int("CFDP_FUSED_SIGNAL", 1);
+  CUDA_CHECK(cudaMalloc(&E.d_progress, 64)); CUDA_CHECK(cudaMemset(E.d_progress, 0, 64)); E.progress_target = 0;
   if (env_int("CFDP_PHASE_PROF", 0)) { CUDA_CHECK(cudaMalloc(&E.pipe.prof, 8 * sizeof(unsigned long long))); CUDA_CHECK(cudaMemset(E.pipe.prof, 0, 8 * sizeof(unsigned long long))); }
   const int smem_limit = 227 * 1024 - 256;
   if (E.kernel_version == 2 && (int)E.pipe.stage_bytes > smem_limit) {
@@ -627,6 +637,21 @@ static void enqueue_exchange(cudaStream_t st)
   launch_rows_copy(E.d_grad, E.d_recv_rows, E.d_recvbuf, nullptr, E.n_recv, CFDP_DIM2, st);      /* threads.c:816-839 */
 }
 
+typedef CUresult (*wait_value64_fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+static wait_value64_fn get_wait_value64(void)
+{
+  static wait_value64_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (wait_value64_fn)p;
+    else (void)cudaGetLastError();
+  }
+  return fn;
+}
+
 static void run_iteration(int variant)
 {
   Engine &E = g_eng;
@@ -635,20 +660,62 @@ static void run_iteration(int variant)
     launch_gradient(0, E.ntiles, E.s_comp);                       /* gradients.c:150-165 */
   } else if (!overlap) {
     launch_gradient(0, E.ntiles, E.s_comp);                       /* bulk synchronous: compute, then exchange (exchange_data_mpi.c:199-284) */
+    if (E.timeline_ek) CUDA_CHECK(cudaEventRecord(E.timeline_ek, E.s_comp));
     enqueue_exchange(E.s_comp);
+    if (E.timeline_ex) CUDA_CHECK(cudaEventRecord(E.timeline_ex, E.s_comp));
   } else {
     /* early send (threads.c:253-346): tiles holding send points first, their rows are packed and
      * shipped on the comm stream while the interior tiles compute */
+    wait_value64_fn wait64 = (E.fused_signal && E.kernel_version == 2) ? get_wait_value64() : nullptr;
+    if (wait64) {
+      /* ONE launch over all tiles; every retired boundary tile bumps a device counter and the comm stream
+       * sleeps on the counter (stream memory operation) -- no split launch, no tail between the two parts */
+      E.progress_target += (unsigned long long)E.nbtiles;
+      launch_gradient(0, E.ntiles, E.s_comp, (int)E.nbtiles);
+      CUresult r = wait64((CUstream)E.s_comm, (CUdeviceptr)E.d_progress, (cuuint64_t)E.progress_target, CU_STREAM_WAIT_VALUE_GEQ);
+      ASSERT(r == CUDA_SUCCESS);
+      if (E.timeline_ek) CUDA_CHECK(cudaEventRecord(E.timeline_ek, E.s_comp));
+      enqueue_exchange(E.s_comm);
+      if (E.timeline_ex) CUDA_CHECK(cudaEventRecord(E.timeline_ex, E.s_comm));
+      CUDA_CHECK(cudaEventRecord(E.ev_x, E.s_comm));
+      CUDA_CHECK(cudaStreamWaitEvent(E.s_comp, E.ev_x, 0));
+      for (Domain *d : E.doms)
+        if (d->cd->ndomains > 1) { d->cd->send_stage++; d->cd->recv_stage++; d->cd->comm_stage++; }
+      return;
+    }
     launch_gradient(0, E.nbtiles, E.s_comp);
     CUDA_CHECK(cudaEventRecord(E.ev_b, E.s_comp));
     CUDA_CHECK(cudaStreamWaitEvent(E.s_comm, E.ev_b, 0));
     enqueue_exchange(E.s_comm);
+    if (E.timeline_ex) CUDA_CHECK(cudaEventRecord(E.timeline_ex, E.s_comm));
     CUDA_CHECK(cudaEventRecord(E.ev_x, E.s_comm));
     launch_gradient(E.nbtiles, E.ntiles - E.nbtiles, E.s_comp);
+    if (E.timeline_ek) CUDA_CHECK(cudaEventRecord(E.timeline_ek, E.s_comp));
     CUDA_CHECK(cudaStreamWaitEvent(E.s_comp, E.ev_x, 0));        /* exchange_dbl_mpi_async waits for all partners before returning */
   }
   for (Domain *d : E.doms)
     if (d->cd->ndomains > 1 && variant != CFDP_COMM_FREE) { d->cd->send_stage++; d->cd->recv_stage++; d->cd->comm_stage++; }
+}
+
+/* debug (CFDP_TIMELINE=1): when, relative to the start of one iteration, the gradient kernel(s) and the
+ * exchange finish */
+static void timeline_probe(int variant)
+{
+  Engine &E = g_eng;
+  cudaEvent_t e0, ek, ex;
+  CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&ek)); CUDA_CHECK(cudaEventCreate(&ex));
+  CUDA_CHECK(cudaDeviceSynchronize());
+  CUDA_CHECK(cudaEventRecord(e0, E.s_comp));
+  CUDA_CHECK(cudaStreamWaitEvent(E.s_comm, e0, 0));
+  E.timeline_ek = ek; E.timeline_ex = ex;
+  run_iteration(variant);
+  E.timeline_ek = nullptr; E.timeline_ex = nullptr;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  float tk = 0, tx = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&tk, e0, ek));
+  if (cudaEventElapsedTime(&tx, e0, ex) != cudaSuccess) { (void)cudaGetLastError(); tx = -1; }
+  fprintf(stderr, "cfdp timeline (variant %d, rank %d): gradient kernel(s) done at %.3f ms, exchange done at %.3f ms\n", variant, E.proc_rank, tk, tx);
+  cudaEventDestroy(e0); cudaEventDestroy(ek); cudaEventDestroy(ex);
 }
 
 extern "C" double cfdp_iterate(int variant, int niter, int final_last)
@@ -657,6 +724,7 @@ extern "C" double cfdp_iterate(int variant, int niter, int final_last)
   Engine &E = g_eng;
   cfdp_commit();
   ASSERT(variant >= CFDP_COMM_FREE && variant <= CFDP_GASPI_ASYNC);
+  if (env_int("CFDP_TIMELINE", 0) && variant != CFDP_COMM_FREE) timeline_probe(variant);
   CUDA_CHECK(cudaEventRecord(E.ev_t0, E.s_comp));
   for (int i = 0; i < niter; i++) run_iteration(variant);
   CUDA_CHECK(cudaEventRecord(E.ev_t1, E.s_comp));
@@ -875,6 +943,7 @@ extern "C" void cfdp_finalize(void)
   }
   E.doms.clear(); E.d_rowmap.clear(); E.point_of_row.clear(); E.peers.clear(); E.send_rows_of.clear(); E.recv_rows_of.clear();
   if (E.pipe.prof) { cudaFree(E.pipe.prof); E.pipe.prof = nullptr; }
+  if (E.d_progress) { cudaFree(E.d_progress); E.d_progress = nullptr; }
   E.d_var = E.d_grad = E.d_pvol = nullptr; E.d_blob = nullptr; E.d_tiles = nullptr; E.d_stage = nullptr;
   E.d_loc_dst = E.d_loc_src = E.d_send_rows = E.d_recv_rows = nullptr; E.d_sendbuf = E.d_recvbuf = nullptr;
   E.committed = false; E.planned = false; E.configured = false;

@@ -147,6 +147,8 @@ struct PipeLayout {
   uint32_t stage_bytes;
   int block_points;  /* threads per CTA (multiple of 32, >= largest tile) */
   unsigned long long *prof; /* optional: SM cycles of thread 0 summed over tiles: [0] wait for data, [1] face walk, [2] rest of the tile, [4] tiles */
+  unsigned long long *progress; /* counts finished boundary tiles (tile index < nsignal): the early-send trigger the comm stream waits on */
+  int nsignal;
 };
 
 __device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes)
@@ -155,6 +157,13 @@ __device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+/* the bulk stores counted by n are complete (wait_group): publish them with one release reduction */
+__device__ __forceinline__ void signal_progress(unsigned long long *ctr, int n)
+{
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(ctr), "l"((unsigned long long)n) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_prev() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 /*
  * Two CTAs per SM, each owning one shared-memory stage and a chunk of consecutive tiles.  Timeline of a tile t:
@@ -238,6 +247,7 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
   }
   __syncthreads(); /* s_hidx may be refilled */
 
+  int pending_sig = 0; /* thread 0: boundary tiles stored but not yet signalled */
   for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
     const bool has_next = t + 1 < t_end;
     stage_pf_index(t + 1); /* lands during the face walk */
@@ -285,7 +295,16 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     if (tid == 0) {
       bulk_s2g(grad + (size_t)td.row0 * (NGRAD * 3), s_nrm, out_rows * (NGRAD * 3 * 8)); /* rows beyond npts are alignment padding */
       bulk_commit();
-      bulk_wait_read(); /* shared memory may be overwritten */
+      bulk_wait_read();      /* shared memory may be overwritten */
+      /* boundary tiles: their rows may be packed / copied by the exchange as soon as every boundary tile has retired
+       * (the reference's finalised-send-point counters, threads.c:268-306).  A CTA reports its boundary tiles in
+       * one go, when it retires or reaches its first interior tile: nobody waits for a write to reach global memory. */
+      if (pending_sig && t >= L.nsignal) {   /* first interior tile of this CTA: flush the signals of its boundary tiles */
+        bulk_wait_prev();    /* every store group but the one just committed is complete */
+        signal_progress(L.progress, pending_sig);
+        pending_sig = 0;
+      }
+      if (t < L.nsignal) pending_sig++;
       if (has_next) {
         if (early) bulk_part(nd, 0, out_end < nd.blob_bytes ? out_end : nd.blob_bytes, false, false);
         else bulk_part(nd, 0, nd.blob_bytes, true, true);
@@ -301,6 +320,10 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
       atomicAdd(L.prof + 0, (unsigned long long)(c1 - c0)); atomicAdd(L.prof + 1, (unsigned long long)(c2 - c1));
       atomicAdd(L.prof + 2, (unsigned long long)(c3 - c2)); atomicAdd(L.prof + 4, 1ull);
     }
+  }
+  if (tid == 0 && pending_sig) {
+    bulk_wait_all();
+    signal_progress(L.progress, pending_sig);
   }
 }
 

@@ -47,6 +47,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+/* L2 eviction policies: the tile blobs and the gradient rows are touched once per iteration (evict first);
+ * the hvar rows are read again by the neighbouring tiles' halo gathers (evict last) */
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -151,9 +170,10 @@ struct PipeLayout {
   int nsignal;
 };
 
-__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes)
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes, uint64_t policy)
 {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -202,6 +222,7 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     fence_mbar_init();
   }
   unsigned char *const st = smem;
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
 
   /* halo row list of tile t (part of its blob) -> s_hidx, asynchronously */
   auto stage_pf_index = [&](int t) {
@@ -218,13 +239,15 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     const uint32_t n_even = CFDP_HALO_BASE((uint32_t)pd.npts);
     const uint32_t nv = n_even * (NGRAD * 8), np = n_even * 8;
     if (announce) mbar_arrive_expect_tx(&full, pd.blob_bytes + nv + np);
-    if (hi > lo) bulk_g2s(st + lo, blob + pd.blob + lo, hi - lo, &full);
+    if (hi > lo) bulk_g2s_hint(st + lo, blob + pd.blob + lo, hi - lo, &full, pol_stream);
     if (with_var) {
-      bulk_g2s(st + tile_var_off(pd.blob_bytes, pd.npts), hvar + (size_t)pd.row0 * NGRAD, nv, &full);
-      bulk_g2s(st + tile_pvol_off(pd.blob_bytes, pd.npts, pd.nhalo), pvol + pd.row0, np, &full);
+      bulk_g2s_hint(st + tile_var_off(pd.blob_bytes, pd.npts), hvar + (size_t)pd.row0 * NGRAD, nv, &full, pol_keep);
+      bulk_g2s_hint(st + tile_pvol_off(pd.blob_bytes, pd.npts, pd.nhalo), pvol + pd.row0, np, &full, pol_stream);
     }
   };
-  /* all threads: hvar rows of the halo points, consecutive lanes = consecutive words of a row */
+  /* all threads: hvar rows of the halo points, consecutive lanes = consecutive words of a row.  (Moving a row as
+   * 16-byte pieces needs the halo position to share the parity of the device row; measured slower: the parity
+   * constraint costs more bank conflicts in the face walk than the shorter gather saves.) */
   auto gather_halo = [&](const TileDesc &pd) {
     double *vs = reinterpret_cast<double *>(st + tile_var_off(pd.blob_bytes, pd.npts)) + (size_t)CFDP_HALO_BASE((uint32_t)pd.npts) * NGRAD;
     const int nw = (int)pd.nhalo * NGRAD;
@@ -293,7 +316,7 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     fence_proxy_async(); /* the staged rows (generic proxy) become visible to the bulk store (async proxy) */
     __syncthreads();     /* S2 */
     if (tid == 0) {
-      bulk_s2g(grad + (size_t)td.row0 * (NGRAD * 3), s_nrm, out_rows * (NGRAD * 3 * 8)); /* rows beyond npts are alignment padding */
+      bulk_s2g(grad + (size_t)td.row0 * (NGRAD * 3), s_nrm, out_rows * (NGRAD * 3 * 8), pol_stream); /* rows beyond npts are alignment padding */
       bulk_commit();
       bulk_wait_read();      /* shared memory may be overwritten */
       /* boundary tiles: their rows may be packed / copied by the exchange as soon as every boundary tile has retired

@@ -180,6 +180,9 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # torchrun exports OMP_NUM_THREADS=1; the setup (mesh generation, face schedule) is OpenMP code: share the host cores
+    if world > 1:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     import numpy as np
     import torch
     import cfd_proxy_b200.mesh as M

@@ -92,6 +92,12 @@ struct PeerPlan {
   int proc = -1;
   long long send_off = 0, send_rows = 0; /* row offsets into the packed send / recv buffers */
   long long recv_off = 0, recv_rows = 0;
+  /* one-sided backend (CUDA IPC): where my rows go in the peer's receive buffer, which of the peer's arrival
+   * counters is mine, and the peer's buffers mapped into this process */
+  long long remote_recv_off = 0, remote_recv_total = 0;
+  int remote_slot = 0;
+  double *peer_recvbuf = nullptr;
+  unsigned long long *peer_flags = nullptr;
 };
 
 struct Engine {
@@ -110,7 +116,9 @@ struct Engine {
   size_t blob_bytes = 0;
   int smem_bytes = 0, region0_doubles = 0, block_threads = 0;
   int kernel_version = 2, chunk = 16, smem_v1 = 0; ggk::PipeLayout pipe = {0, 256, nullptr, nullptr, 0};
-  unsigned long long *d_progress = nullptr; unsigned long long progress_target = 0; int fused_signal = 1; uint32_t max_footprint = 0;
+  unsigned long long *d_progress = nullptr; unsigned long long progress_target = 0; int fused_signal = 1;
+  /* one-sided exchange: double-buffered receive window + per-peer arrival counters (exchange_data_gaspi.c:105-151) */
+  bool ipc_ready = false; double *d_recvwin = nullptr; unsigned long long *d_arrived = nullptr; unsigned long long ipc_stage = 0; uint32_t max_footprint = 0;
   size_t max_blob = 0; int max_nhalo = 0;
   std::vector<int *> d_rowmap;     /* per hosted domain: [nall] global device row of host point */
   double *d_stage = nullptr; size_t stage_bytes = 0;
@@ -353,11 +361,13 @@ static void launch_rows_copy(double *dst, const uint32_t *dst_rows, const double
                              long long nrows, int width, cudaStream_t st, double scale = 1.0)
 {
   if (nrows <= 0) return;
+  /* 64-thread blocks: small enough (registers) to become resident next to two gradient CTAs, so that pack / unpack
+   * of the overlapped exchange do not have to wait for a gradient CTA to retire */
   const long long total = nrows * width;
-  long long blocks = (total + 255) / 256;
-  static const long long cap = env_int("CFDP_COPY_BLOCKS", 148 * 16);
+  long long blocks = (total + 63) / 64;
+  static const long long cap = env_int("CFDP_COPY_BLOCKS", 148 * 32);
   if (blocks > cap) blocks = cap;
-  rows_copy_kernel<<<(unsigned)blocks, 256, 0, st>>>(dst, dst_rows, src, src_rows, nrows, width, scale);
+  rows_copy_kernel<<<(unsigned)blocks, 64, 0, st>>>(dst, dst_rows, src, src_rows, nrows, width, scale);
   CUDA_CHECK(cudaGetLastError());
   g_eng.launches++;
 }
@@ -506,6 +516,8 @@ extern "C" void cfdp_plan(void)
   E.planned = true;
 }
 
+static void ipc_setup(void);
+
 /* device part: allocate, upload, configure the kernel */
 extern "C" void cfdp_commit(void)
 {
@@ -574,7 +586,8 @@ extern "C" void cfdp_commit(void)
   E.d_send_rows = upload(E.h_send_rows); E.d_recv_rows = upload(E.h_recv_rows);
   CUDA_CHECK(cudaMalloc(&E.d_sendbuf, (size_t)std::max<long long>(E.n_send, 1) * CFDP_DIM2 * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&E.d_recvbuf, (size_t)std::max<long long>(E.n_recv, 1) * CFDP_DIM2 * sizeof(double)));
-  if (!E.peers.empty() && !E.comm) nccl_file_bootstrap();
+  if (!E.peers.empty() && !E.comm && !g_int_exchange) nccl_file_bootstrap();
+  if (!E.peers.empty() && env_int("CFDP_IPC", 1)) ipc_setup();
   CUDA_CHECK(cudaDeviceSynchronize());
   E.committed = true;
   /* var as it stands in the host containers */
@@ -621,6 +634,89 @@ extern "C" void cfdp_grad_to_host(solver_data *sd)
  * ---------------------------------------------------------------------------------------- */
 static bool have_exchange(void) { return g_eng.n_local > 0 || !g_eng.peers.empty(); }
 
+/* ------------------------------------------------------------------------------------------
+ * One-sided backend: put + notify over CUDA IPC (the GASPI write_notify / MPI_Put model,
+ * exchange_data_gaspi.c:105-151, exchange_data_mpidma.c:93-127).  Every rank owns a receive window of two
+ * stages (double buffered by stage parity like the reference's segments, exchange_data_gaspi.c:181,230) and one
+ * arrival counter per peer.  A sender copies its packed rows straight into the peer's window at the offset the
+ * peer told it at setup (remote_recv_offset, comm_data.c:355-396) -- a device-to-device copy over NVLink that
+ * needs no SM -- and then bumps its counter in the peer's memory; the receiver's stream sleeps on its own
+ * counter (stream memory operation), then unpacks.  No kernel ever spins.
+ * ---------------------------------------------------------------------------------------- */
+__global__ void notify_kernel(unsigned long long *flag, unsigned long long value)
+{
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long *>(flag) = value;
+  __threadfence_system();
+}
+
+static void ipc_setup(void)
+{
+  Engine &E = g_eng;
+  if (E.ipc_ready || E.peers.empty()) return;
+  const size_t np = E.peers.size();
+  CUDA_CHECK(cudaMalloc(&E.d_recvwin, (size_t)std::max<long long>(E.n_recv, 1) * 2 * CFDP_DIM2 * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&E.d_arrived, 256 * sizeof(unsigned long long)));
+  CUDA_CHECK(cudaMemset(E.d_arrived, 0, 256 * sizeof(unsigned long long)));
+  ASSERT(np <= 256);
+  cudaIpcMemHandle_t hwin, hflag;
+  CUDA_CHECK(cudaIpcGetMemHandle(&hwin, E.d_recvwin));
+  CUDA_CHECK(cudaIpcGetMemHandle(&hflag, E.d_arrived));
+  const int HW = (int)(sizeof(cudaIpcMemHandle_t) / sizeof(int)); /* 16 */
+  const int MSG = 2 * HW + 5;
+  std::vector<std::vector<int>> sb(np, std::vector<int>((size_t)MSG)), rb(np, std::vector<int>((size_t)MSG));
+  std::vector<int> peer; std::vector<const int *> sp; std::vector<int> sc; std::vector<int *> rp; std::vector<int> rc;
+  for (size_t i = 0; i < np; i++) {
+    memcpy(sb[i].data(), &hwin, sizeof hwin); memcpy(sb[i].data() + HW, &hflag, sizeof hflag);
+    sb[i][2 * HW + 0] = (int)(E.peers[i].recv_off & 0x7FFFFFFF); sb[i][2 * HW + 1] = (int)(E.peers[i].recv_off >> 31);
+    sb[i][2 * HW + 2] = (int)i;                                   /* the counter this peer bumps */
+    sb[i][2 * HW + 3] = (int)(E.n_recv & 0x7FFFFFFF); sb[i][2 * HW + 4] = (int)(E.n_recv >> 31);
+    peer.push_back(E.peers[i].proc); sp.push_back(sb[i].data()); sc.push_back(MSG); rp.push_back(nullptr); rc.push_back(0);
+  }
+  for (size_t i = 0; i < np; i++) { peer.push_back(E.peers[i].proc); sp.push_back(nullptr); sc.push_back(0); rp.push_back(rb[i].data()); rc.push_back(MSG); }
+  engine_exchange_ints(peer, sp, sc, rp, rc);
+  for (size_t i = 0; i < np; i++) {
+    PeerPlan &p = E.peers[i];
+    cudaIpcMemHandle_t h1, h2;
+    memcpy(&h1, rb[i].data(), sizeof h1); memcpy(&h2, rb[i].data() + HW, sizeof h2);
+    void *w = nullptr, *f = nullptr;
+    CUDA_CHECK(cudaIpcOpenMemHandle(&w, h1, cudaIpcMemLazyEnablePeerAccess));
+    CUDA_CHECK(cudaIpcOpenMemHandle(&f, h2, cudaIpcMemLazyEnablePeerAccess));
+    p.peer_recvbuf = (double *)w; p.peer_flags = (unsigned long long *)f;
+    p.remote_recv_off = (long long)rb[i][2 * HW + 0] | ((long long)rb[i][2 * HW + 1] << 31);
+    p.remote_slot = rb[i][2 * HW + 2];
+    p.remote_recv_total = (long long)rb[i][2 * HW + 3] | ((long long)rb[i][2 * HW + 4] << 31);
+  }
+  E.ipc_ready = true;
+}
+
+static CUresult stream_wait_geq(cudaStream_t st, const void *addr, unsigned long long value);
+
+static void enqueue_exchange_onesided(cudaStream_t st)
+{
+  Engine &E = g_eng;
+  launch_rows_copy(E.d_grad, E.d_loc_dst, E.d_grad, E.d_loc_src, E.n_local, CFDP_DIM2, st);
+  if (E.peers.empty()) return;
+  const unsigned long long stage = E.ipc_stage++;
+  const int half = (int)(stage & 1);                                                               /* exchange_data_gaspi.c:181 */
+  launch_rows_copy(E.d_sendbuf, nullptr, E.d_grad, E.d_send_rows, E.n_send, CFDP_DIM2, st);      /* threads.c:791-813 */
+  for (const PeerPlan &p : E.peers) {
+    if (!p.send_rows) continue;
+    double *dst = p.peer_recvbuf + ((size_t)half * (size_t)p.remote_recv_total + (size_t)p.remote_recv_off) * CFDP_DIM2;
+    CUDA_CHECK(cudaMemcpyAsync(dst, E.d_sendbuf + p.send_off * CFDP_DIM2, (size_t)p.send_rows * CFDP_DIM2 * sizeof(double),
+                               cudaMemcpyDeviceToDevice, st));                                      /* gaspi_write ... */
+    notify_kernel<<<1, 1, 0, st>>>(p.peer_flags + p.remote_slot, stage + 1);                        /* ... _notify */
+    CUDA_CHECK(cudaGetLastError());
+    E.launches++;
+  }
+  for (size_t i = 0; i < E.peers.size(); i++) {                                                     /* gaspi_notify_waitsome, exchange_data_gaspi.c:252-262 */
+    if (!E.peers[i].recv_rows) continue;
+    CUresult r = stream_wait_geq(st, E.d_arrived + i, stage + 1);
+    ASSERT(r == CUDA_SUCCESS);
+  }
+  launch_rows_copy(E.d_grad, E.d_recv_rows, E.d_recvwin + (size_t)half * (size_t)E.n_recv * CFDP_DIM2, nullptr, E.n_recv, CFDP_DIM2, st);
+}
+
 static void enqueue_exchange(cudaStream_t st)
 {
   Engine &E = g_eng;
@@ -652,6 +748,20 @@ static wait_value64_fn get_wait_value64(void)
   return fn;
 }
 
+static CUresult stream_wait_geq(cudaStream_t st, const void *addr, unsigned long long value)
+{
+  wait_value64_fn fn = get_wait_value64();
+  if (!fn) return CUDA_ERROR_NOT_SUPPORTED;
+  return fn((CUstream)st, (CUdeviceptr)addr, (cuuint64_t)value, CU_STREAM_WAIT_VALUE_GEQ);
+}
+
+static void enqueue_exchange_for(int variant, cudaStream_t st)
+{
+  Engine &E = g_eng;
+  const bool onesided = (variant == CFDP_GASPI_BULK_SYNC || variant == CFDP_GASPI_ASYNC) && E.ipc_ready && get_wait_value64();
+  if (onesided) enqueue_exchange_onesided(st); else enqueue_exchange(st);
+}
+
 static void run_iteration(int variant)
 {
   Engine &E = g_eng;
@@ -661,7 +771,7 @@ static void run_iteration(int variant)
   } else if (!overlap) {
     launch_gradient(0, E.ntiles, E.s_comp);                       /* bulk synchronous: compute, then exchange (exchange_data_mpi.c:199-284) */
     if (E.timeline_ek) CUDA_CHECK(cudaEventRecord(E.timeline_ek, E.s_comp));
-    enqueue_exchange(E.s_comp);
+    enqueue_exchange_for(variant, E.s_comp);
     if (E.timeline_ex) CUDA_CHECK(cudaEventRecord(E.timeline_ex, E.s_comp));
   } else {
     /* early send (threads.c:253-346): tiles holding send points first, their rows are packed and
@@ -675,7 +785,7 @@ static void run_iteration(int variant)
       CUresult r = wait64((CUstream)E.s_comm, (CUdeviceptr)E.d_progress, (cuuint64_t)E.progress_target, CU_STREAM_WAIT_VALUE_GEQ);
       ASSERT(r == CUDA_SUCCESS);
       if (E.timeline_ek) CUDA_CHECK(cudaEventRecord(E.timeline_ek, E.s_comp));
-      enqueue_exchange(E.s_comm);
+      enqueue_exchange_for(variant, E.s_comm);
       if (E.timeline_ex) CUDA_CHECK(cudaEventRecord(E.timeline_ex, E.s_comm));
       CUDA_CHECK(cudaEventRecord(E.ev_x, E.s_comm));
       CUDA_CHECK(cudaStreamWaitEvent(E.s_comp, E.ev_x, 0));
@@ -686,7 +796,7 @@ static void run_iteration(int variant)
     launch_gradient(0, E.nbtiles, E.s_comp);
     CUDA_CHECK(cudaEventRecord(E.ev_b, E.s_comp));
     CUDA_CHECK(cudaStreamWaitEvent(E.s_comm, E.ev_b, 0));
-    enqueue_exchange(E.s_comm);
+    enqueue_exchange_for(variant, E.s_comm);
     if (E.timeline_ex) CUDA_CHECK(cudaEventRecord(E.timeline_ex, E.s_comm));
     CUDA_CHECK(cudaEventRecord(E.ev_x, E.s_comm));
     launch_gradient(E.nbtiles, E.ntiles - E.nbtiles, E.s_comp);
@@ -923,6 +1033,10 @@ extern "C" void cfdp_finalize(void)
     cudaFree(E.d_loc_dst); cudaFree(E.d_loc_src); cudaFree(E.d_send_rows); cudaFree(E.d_recv_rows); cudaFree(E.d_sendbuf); cudaFree(E.d_recvbuf);
     for (int *p : E.d_rowmap) cudaFree(p);
   }
+  if (E.ipc_ready) {
+    for (PeerPlan &p : E.peers) { if (p.peer_recvbuf) cudaIpcCloseMemHandle(p.peer_recvbuf); if (p.peer_flags) cudaIpcCloseMemHandle(p.peer_flags); }
+    cudaFree(E.d_recvwin); cudaFree(E.d_arrived); E.d_recvwin = nullptr; E.d_arrived = nullptr; E.ipc_ready = false; E.ipc_stage = 0;
+  }
   for (Domain *d : E.doms) {
     /* host containers this library allocated (read_solver_data / read_communication_data / cfdp_attach_mesh) */
     if (d->sd) {
@@ -944,6 +1058,7 @@ extern "C" void cfdp_finalize(void)
   E.doms.clear(); E.d_rowmap.clear(); E.point_of_row.clear(); E.peers.clear(); E.send_rows_of.clear(); E.recv_rows_of.clear();
   if (E.pipe.prof) { cudaFree(E.pipe.prof); E.pipe.prof = nullptr; }
   if (E.d_progress) { cudaFree(E.d_progress); E.d_progress = nullptr; }
+
   E.d_var = E.d_grad = E.d_pvol = nullptr; E.d_blob = nullptr; E.d_tiles = nullptr; E.d_stage = nullptr;
   E.d_loc_dst = E.d_loc_src = E.d_send_rows = E.d_recv_rows = nullptr; E.d_sendbuf = E.d_recvbuf = nullptr;
   E.committed = false; E.planned = false; E.configured = false;

@@ -28,7 +28,7 @@ def main():
     S.load_spec(spec)
     S.setup()
     errors = []
-    for variant in ("mpi_bulk_sync", "mpi_early_recv", "mpi_async", "gaspi_async"):
+    for variant in ("mpi_bulk_sync", "mpi_early_recv", "mpi_async", "gaspi_bulk_sync", "gaspi_async"):  # gaspi_* = CUDA-IPC put + notify
         for d in S.domains:
             d.grad[:] = np.nan
         S.lib.cfdp_set_resident(1)

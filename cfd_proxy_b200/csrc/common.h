@@ -91,11 +91,9 @@ struct Domain {
   comm_data *cd = nullptr;
   solver_data *sd = nullptr;
   bool comm_read = false, tables_done = false, threads_inited = false;
-  bool host_pinned = false;    /* var/grad were allocated by this library as pinned memory */
   DomainSchedule sch;
   long long rowbase = 0;       /* first device row of this domain */
   long long tile0_b = 0, tile0_i = 0; /* first boundary / interior tile in the global tile list */
-  std::vector<int> ncpath;     /* unused */
 };
 
 /* engine.cu */

@@ -7,14 +7,12 @@
  * the point, walks its incident faces in the reference's single-thread order and keeps the 7x3
  * sums in registers: no atomics, no read of grad, one 168-byte row store per point.
  *
- * gg_tile_pipe_kernel (the production kernel): a CTA processes a chunk of consecutive tiles
- * through a two-stage shared-memory ring.  Per tile, ONE elected thread issues three TMA bulk
- * copies (cp.async.bulk global->shared, mbarrier complete_tx): the tile blob (face normals read
- * once, halo row list, ELL adjacency), the contiguous var rows and volumes of the tile's own
- * points; all threads gather the var rows of the tile's halo points with 8-byte cp.async
- * (LDGSTS) tracked by the same mbarrier.  The loads of tile t+2 are issued when tile t retires,
- * so they fly while tile t+1 computes; HBM is only touched by asynchronous copies and by the
- * coalesced 16-byte row stores.
+ * gg_tile_pipe_kernel (the production kernel): two CTAs per SM, each walking a chunk of consecutive tiles through
+ * one shared-memory stage.  Per tile ONE elected thread issues the TMA bulk copies (cp.async.bulk global->shared,
+ * mbarrier complete_tx): the tile blob (face normals read once, halo row list, ELL adjacency), the contiguous hvar
+ * rows and volumes of the tile's own points; all threads gather the hvar rows of the tile's halo points with 8-byte
+ * cp.async (LDGSTS) tracked by the same mbarrier.  The next tile is fetched as soon as the face walk of the
+ * current one is over, the result rows leave through one TMA bulk store: HBM is only touched by asynchronous copies.
  *
  * Arithmetic modes
  *   EXACT = true : separate IEEE multiply and add in the reference's order.  The device holds

@@ -210,6 +210,116 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
     for (int t = 0; t < ntiles; t++) std::sort(tb.pts.begin() + tb.tile_pt_off[t], tb.pts.begin() + tb.tile_pt_off[(size_t)t + 1]);
   }
 
+  /* ---- 1b. own rows by shared-memory bank.  A tile point is a lane of the face walk AND a var row other lanes
+   * gather.  Permuting the points inside a block of 16 consecutive positions keeps every half-warp's membership (so
+   * the sets of rows read together do not change) but lets each point pick the bank-pair class (position mod 16)
+   * that collides least with the other rows of the groups it is gathered in.  Halo rows and face slots are placed
+   * afterwards against these fixed own rows (pass B). */
+  if (opt.bank_placement) {
+    const int nthr0 = omp_get_max_threads();
+    std::vector<std::vector<int>> lmap0((size_t)nthr0);
+#pragma omp parallel
+    {
+      std::vector<int> &lmap = lmap0[omp_get_thread_num()];
+      lmap.assign((size_t)nall, -1);
+      struct Key { int tt, p1, p0, face, nb; };
+      std::vector<Key> keys;
+      std::vector<int> nbr_of, deg, goff, glist, fill, newP;
+      std::vector<unsigned char> cnt, gmax;
+#pragma omp for schedule(dynamic, 16)
+      for (int t = 0; t < ntiles; t++) {
+        int *P = &tb.pts[tb.tile_pt_off[t]];
+        const int n = (int)(tb.tile_pt_off[(size_t)t + 1] - tb.tile_pt_off[t]);
+        if (n <= 16) continue;
+        int md = 0;
+        for (int i = 0; i < n; i++) { lmap[P[i]] = i; md = std::max(md, (int)(g.off[(size_t)P[i] + 1] - g.off[P[i]])); }
+        nbr_of.assign((size_t)n * md, -1); deg.assign((size_t)n, 0);
+        for (int i = 0; i < n; i++) {
+          const int p = P[i];
+          keys.clear();
+          for (long long a = g.off[p]; a < g.off[(size_t)p + 1]; a++) {
+            const int q = g.nbr[a];
+            const int p0 = g.sign[a] ? q : p, p1 = g.sign[a] ? p : q;
+            const int h0 = p0 >= nown ? 3 : (is_send[p0] ? 2 : 1), h1 = p1 >= nown ? 3 : (is_send[p1] ? 2 : 1);
+            keys.push_back(Key{((h0 == 2 || h1 == 2) ? 0 : 3) + (h0 == 3 ? 0 : (h1 == 3 ? 1 : 2)), p1, p0, g.face[a], lmap[q]});
+          }
+          std::sort(keys.begin(), keys.end(), [](const Key &x, const Key &y) {
+            if (x.tt != y.tt) return x.tt < y.tt;
+            if (x.p1 != y.p1) return x.p1 < y.p1;
+            if (x.p0 != y.p0) return x.p0 < y.p0;
+            return x.face < y.face;
+          });
+          deg[i] = (int)keys.size();
+          for (size_t j = 0; j < keys.size(); j++) nbr_of[(size_t)i * md + j] = keys[j].nb;
+        }
+        /* row r -> distinct groups (half-warp of the reader, step) it is read in */
+        goff.assign((size_t)n + 1, 0);
+        for (int pass = 0; pass < 2; pass++) {
+          if (pass == 1) { for (int r = 0; r < n; r++) goff[(size_t)r + 1] += goff[r]; glist.assign((size_t)goff[n], -1); fill.assign(goff.begin(), goff.end() - 1); }
+          for (int i = 0; i < n; i++)
+            for (int j = 0; j < deg[i]; j++) {
+              const int r = nbr_of[(size_t)i * md + j];
+              if (r < 0) continue;
+              const int gi = (i / 16) * md + j;
+              if (pass == 0) goff[(size_t)r + 1]++;
+              else {
+                bool dup = false;
+                for (int x = goff[r]; x < fill[r]; x++) if (glist[x] == gi) dup = true;
+                if (!dup) glist[fill[r]++] = gi;
+              }
+            }
+        }
+        const int ngrp = ((n + 15) / 16) * md;
+        cnt.assign((size_t)ngrp * 16, 0); gmax.assign((size_t)ngrp, 0);
+        newP.assign((size_t)n, -1);
+        for (int b0 = 0; b0 < n; b0 += 16) {
+          const int m = std::min(16, n - b0);
+          unsigned used = 0;
+          for (int i = b0; i < b0 + m; i++) {
+            int best = -1, best_cost = 1 << 30;
+            for (int c0 = 0; c0 < m; c0++) {
+              const int c = (c0 + i) % m;
+              if (used & (1u << c)) continue;
+              int cost = 0;
+              for (int x = goff[i]; x < goff[(size_t)i + 1]; x++) {
+                const int gi = glist[x];
+                if (gi < 0) continue;
+                const int cc = cnt[(size_t)gi * 16 + c];
+                cost += (cc + 1 > gmax[gi] ? 4 : 0) + cc;
+              }
+              if (cost < best_cost) { best_cost = cost; best = c; }
+            }
+            used |= 1u << best;
+            newP[(size_t)b0 + best] = P[i];
+            for (int x = goff[i]; x < goff[(size_t)i + 1]; x++) {
+              const int gi = glist[x];
+              if (gi < 0) continue;
+              unsigned char &cc = cnt[(size_t)gi * 16 + best];
+              cc++;
+              if (cc > gmax[gi]) gmax[gi] = cc;
+            }
+          }
+        }
+        for (int i = 0; i < n; i++) lmap[P[i]] = -1;
+        /* keep the permutation only where it beats the file order (structured numberings are already good) */
+        long long after = 0, before = 0;
+        for (int gi = 0; gi < ngrp; gi++) after += gmax[gi];
+        cnt.assign((size_t)ngrp * 16, 0); gmax.assign((size_t)ngrp, 0);
+        for (int r = 0; r < n; r++)
+          for (int x = goff[r]; x < goff[(size_t)r + 1]; x++) {
+            const int gi = glist[x];
+            if (gi < 0) continue;
+            unsigned char &cc = cnt[(size_t)gi * 16 + (r & 15)];
+            cc++;
+            if (cc > gmax[gi]) gmax[gi] = cc;
+          }
+        for (int gi = 0; gi < ngrp; gi++) before += gmax[gi];
+        if (after * 100 < before * 85)
+          for (int i = 0; i < n; i++) { ASSERT(newP[i] >= 0); P[i] = newP[i]; }
+      }
+    }
+  }
+
   /* ---- 2. boundary tiles first, rows ---- */
   std::vector<int> tile_bnd((size_t)ntiles, 0), order((size_t)ntiles);
   for (int t = 0; t < ntiles; t++)

@@ -680,8 +680,13 @@ static void ipc_setup(void)
     cudaIpcMemHandle_t h1, h2;
     memcpy(&h1, rb[i].data(), sizeof h1); memcpy(&h2, rb[i].data() + HW, sizeof h2);
     void *w = nullptr, *f = nullptr;
-    CUDA_CHECK(cudaIpcOpenMemHandle(&w, h1, cudaIpcMemLazyEnablePeerAccess));
-    CUDA_CHECK(cudaIpcOpenMemHandle(&f, h2, cudaIpcMemLazyEnablePeerAccess));
+    if (cudaIpcOpenMemHandle(&w, h1, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&f, h2, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      /* no peer mapping between these GPUs: the one-sided variant names keep using the NCCL transport */
+      fprintf(stderr, "cfdp: CUDA IPC mapping of rank %d's window failed (%s); one-sided variants fall back to NCCL\n",
+              p.proc, cudaGetErrorString(cudaGetLastError()));
+      return;
+    }
     p.peer_recvbuf = (double *)w; p.peer_flags = (unsigned long long *)f;
     p.remote_recv_off = (long long)rb[i][2 * HW + 0] | ((long long)rb[i][2 * HW + 1] << 31);
     p.remote_slot = rb[i][2 * HW + 2];

@@ -14,6 +14,9 @@ def main():
         mp = float(args[1]); args = args[2:]
     n = lattice_for(mp)
     peak, _ = measured_peak()
+    f6 = None
+    if args and args[0].startswith("--f6like"):
+        f6 = int(args[0][8:]); args = args[1:]
     for cfg in args:
         parts = cfg.split(":") + ["2", "2"]
         k, tile, chunk, fma, order, stages, split = parts[:7]
@@ -22,8 +25,11 @@ def main():
         os.environ["CFDP_STAGES"] = stages
         os.environ["CFDP_SPLIT"] = split
         t0 = time.time()
-        with Session(8, device=0, tile_points=int(tile), tile_order=1 if order == "brickid" else 0) as S:
-            spec = M.make_spec(n, (2, 2, 2), order="brick" if order.startswith("brick") else order, brick=8, jitter=0.1, allow_big=True)
+        with Session(f6 or 8, device=0, tile_points=int(tile), tile_order=1 if order == "brickid" else 0) as S:
+            if f6:   # BASELINE configs[1]/[2]: F6-like stand-in (hybrid hex/tet dual, ~2 M points at level 1), all domains on one GPU
+                spec = M.f6like_spec(f6, lvl=1, order=order)
+            else:
+                spec = M.make_spec(n, (2, 2, 2), order="brick" if order.startswith("brick") else order, brick=8, jitter=0.1, allow_big=True)
             S.load_spec(spec); S.setup()
             S.lib.cfdp_set_exact(0 if fma == "1" else 1)
             S.iterate("comm_free", 3)

@@ -228,6 +228,8 @@ extern "C" int cfdp_configure(int proc_rank, int nprocs, int ndomains_total, int
   E.sopt.order = env_int("CFDP_TILE_ORDER", 0);
   E.sopt.sort_in_tile = env_int("CFDP_SORT_IN_TILE", 1);
   E.sopt.bank_placement = env_int("CFDP_BANK_PLACEMENT", 1);
+  E.sopt.slack_slots = env_int("CFDP_SLACK_SLOTS", 0);
+  E.sopt.slack_halo = env_int("CFDP_SLACK_HALO", 0);
   E.sopt.stage_budget = env_int("CFDP_STAGE_BUDGET", 105 * 1024); /* two tiles (two CTAs or two stages) in 228 KB of shared memory per SM */
   E.exact = env_int("CFDP_EXACT", 1);
   E.configured = true;

@@ -105,9 +105,11 @@ template <bool EXACT, int LO, int CNT>
 __device__ __forceinline__ void walk_faces(const uint32_t *__restrict__ ell, int npad, int maxdeg, const double *__restrict__ s_nrm,
                                            const double *__restrict__ s_hvar, const double (&hv)[CNT], double (&acc)[CNT * 3])
 {
+  uint32_t e_next = maxdeg > 0 ? ell[0] : CFDP_ADJ_PAD;
 #pragma unroll 2
   for (int j = 0; j < maxdeg; j++) {
-    const uint32_t e = ell[j * npad];
+    const uint32_t e = e_next;                                    /* the adjacency entry is fetched one step ahead */
+    e_next = j + 1 < maxdeg ? ell[(j + 1) * npad] : CFDP_ADJ_PAD;
     if (e == CFDP_ADJ_PAD) continue;
     const double *n = s_nrm + 3 * ((e >> 16) & 0x7FFFu);
     const double *w = s_hvar + NGRAD * (e & 0xFFFFu) + LO;

@@ -87,7 +87,7 @@ struct TileBuilder {
   size_t footprint(int np_, int nf_, int nh_, int md_) const
   {
     const uint32_t npad = (uint32_t)align_up((size_t)np_, 32);
-    nf_ = (int)align_up((size_t)nf_, 16); nh_ = (int)align_up((size_t)nh_, 16);
+    nf_ = (int)align_up((size_t)nf_ + (size_t)opt.slack_slots, 16); nh_ = (int)align_up((size_t)nh_ + (size_t)opt.slack_halo, 16);
     return align_up(std::max(blob_size((uint32_t)nf_, (uint32_t)nh_, (uint32_t)md_, npad), (size_t)np_ * CFDP_DIM2 * 8), 128) +
            align_up((size_t)(CFDP_HALO_BASE(np_) + nh_) * NGRAD * 8, 128) + align_up((size_t)CFDP_HALO_BASE(np_) * 8, 128);
   }
@@ -389,7 +389,8 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
       for (int q : halo_local) lmap[q] = -1;
       out.tile_nfaces[k] = nf; tnh[k] = nh; tmaxdeg[k] = md;
       /* shared-memory positions: 16 residue classes of equal size, so that slots / rows can be placed by bank */
-      out.tile_nslots[k] = (int)align_up((size_t)nf, 16); out.tile_nhpos[k] = (int)align_up((size_t)nh, 16);
+      /* a little slack lets the bank placement avoid forced collisions when a class fills up */
+      out.tile_nslots[k] = (int)align_up((size_t)nf + (size_t)opt.slack_slots, 16); out.tile_nhpos[k] = (int)align_up((size_t)nh + (size_t)opt.slack_halo, 16);
       ASSERT(out.tile_nslots[k] <= 32767 && n + 1 + out.tile_nhpos[k] <= 65534);
     }
   }

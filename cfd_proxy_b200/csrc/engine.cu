@@ -852,14 +852,118 @@ extern "C" double cfdp_iterate(int variant, int niter, int final_last)
   return (double)ms;
 }
 
+/*
+ * One drop-in step with HOST buffers: sd->var in, sd->grad out (the reference's calling convention).  PCIe is the
+ * bottleneck (56 B up, 168 B down per point), so the hosted domains are pipelined over three streams: while domain
+ * d+1 uploads, domain d computes and the own rows of domain d-1 go back; both PCIe directions are busy at once.
+ * Ghost rows follow after the exchange: they are contiguous at the end of both the host array and the domain's
+ * device rows, so they need no gather.
+ */
+struct E2EResources {
+  bool ready = false;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  double *var_stage[2] = {nullptr, nullptr}, *grad_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_up[2], ev_var_free[2], ev_gath[2], ev_grad_free[2], ev_begin, ev_x, ev_end;
+};
+static E2EResources g_e2e;
+
+static void e2e_setup(void)
+{
+  Engine &E = g_eng;
+  if (g_e2e.ready) return;
+  size_t max_var = 0, max_grad = 0;
+  for (Domain *d : E.doms) {
+    max_var = std::max(max_var, (size_t)d->sch.nall * NGRAD * sizeof(double));
+    max_grad = std::max(max_grad, (size_t)d->sch.nown * CFDP_DIM2 * sizeof(double));
+  }
+  CUDA_CHECK(cudaStreamCreateWithFlags(&g_e2e.s_h2d, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&g_e2e.s_d2h, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; b++) {
+    CUDA_CHECK(cudaMalloc(&g_e2e.var_stage[b], max_var));
+    CUDA_CHECK(cudaMalloc(&g_e2e.grad_stage[b], max_grad));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_e2e.ev_up[b], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_e2e.ev_var_free[b], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_e2e.ev_gath[b], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_e2e.ev_grad_free[b], cudaEventDisableTiming));
+  }
+  CUDA_CHECK(cudaEventCreateWithFlags(&g_e2e.ev_begin, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&g_e2e.ev_x, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&g_e2e.ev_end, cudaEventDisableTiming));
+  g_e2e.ready = true;
+}
+
+static void e2e_release(void)
+{
+  if (!g_e2e.ready) return;
+  cudaStreamDestroy(g_e2e.s_h2d); cudaStreamDestroy(g_e2e.s_d2h);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(g_e2e.var_stage[b]); cudaFree(g_e2e.grad_stage[b]);
+    cudaEventDestroy(g_e2e.ev_up[b]); cudaEventDestroy(g_e2e.ev_var_free[b]); cudaEventDestroy(g_e2e.ev_gath[b]); cudaEventDestroy(g_e2e.ev_grad_free[b]);
+  }
+  cudaEventDestroy(g_e2e.ev_begin); cudaEventDestroy(g_e2e.ev_x); cudaEventDestroy(g_e2e.ev_end);
+  g_e2e = E2EResources();
+}
+
+/* enqueue one pipelined host-buffer step; the caller synchronises on s_comp */
+static void enqueue_step_e2e(int variant)
+{
+  Engine &E = g_eng;
+  e2e_setup();
+  E2EResources &R = g_e2e;
+  const bool exchange = variant != CFDP_COMM_FREE && have_exchange();
+  CUDA_CHECK(cudaEventRecord(R.ev_begin, E.s_comp));
+  CUDA_CHECK(cudaStreamWaitEvent(R.s_h2d, R.ev_begin, 0));
+  CUDA_CHECK(cudaStreamWaitEvent(R.s_d2h, R.ev_begin, 0));
+  const int nh = (int)E.doms.size();
+  for (int i = 0; i < nh; i++) {
+    Domain *d = E.doms[(size_t)i];
+    solver_data *sd = d->sd;
+    const int b = i & 1;
+    const size_t nall = (size_t)sd->nallpoints, nown = (size_t)sd->nownpoints;
+    /* up: var of this domain (own + ghost rows, host order) */
+    if (i >= 2) CUDA_CHECK(cudaStreamWaitEvent(R.s_h2d, R.ev_var_free[b], 0));
+    CUDA_CHECK(cudaMemcpyAsync(R.var_stage[b], &sd->var[0][0], nall * NGRAD * sizeof(double), cudaMemcpyHostToDevice, R.s_h2d));
+    CUDA_CHECK(cudaEventRecord(R.ev_up[b], R.s_h2d));
+    /* compute: permute into device rows (halved), this domain's boundary and interior tiles */
+    CUDA_CHECK(cudaStreamWaitEvent(E.s_comp, R.ev_up[b], 0));
+    launch_rows_copy(E.d_var, (const uint32_t *)E.d_rowmap[(size_t)i], R.var_stage[b], nullptr, (long long)nall, NGRAD, E.s_comp, 0.5);
+    CUDA_CHECK(cudaEventRecord(R.ev_var_free[b], E.s_comp));
+    launch_gradient(d->tile0_b, d->sch.nboundary, E.s_comp);
+    launch_gradient(d->tile0_i, d->sch.ntiles - d->sch.nboundary, E.s_comp);
+    /* down: own rows back in host order */
+    if (i >= 2) CUDA_CHECK(cudaStreamWaitEvent(E.s_comp, R.ev_grad_free[b], 0));
+    launch_rows_copy(R.grad_stage[b], nullptr, E.d_grad, (const uint32_t *)E.d_rowmap[(size_t)i], (long long)nown, CFDP_DIM2, E.s_comp);
+    CUDA_CHECK(cudaEventRecord(R.ev_gath[b], E.s_comp));
+    CUDA_CHECK(cudaStreamWaitEvent(R.s_d2h, R.ev_gath[b], 0));
+    CUDA_CHECK(cudaMemcpyAsync(&sd->grad[0][0][0], R.grad_stage[b], nown * CFDP_DIM2 * sizeof(double), cudaMemcpyDeviceToHost, R.s_d2h));
+    CUDA_CHECK(cudaEventRecord(R.ev_grad_free[b], R.s_d2h));
+  }
+  if (exchange) {
+    /* every domain's rows are final: halo exchange, then the ghost rows (contiguous on both sides) */
+    enqueue_exchange_for(variant, E.s_comp);
+    CUDA_CHECK(cudaEventRecord(R.ev_x, E.s_comp));
+    CUDA_CHECK(cudaStreamWaitEvent(R.s_d2h, R.ev_x, 0));
+    for (int i = 0; i < nh; i++) {
+      Domain *d = E.doms[(size_t)i];
+      solver_data *sd = d->sd;
+      const size_t nadd = (size_t)(sd->nallpoints - sd->nownpoints);
+      if (!nadd) continue;
+      CUDA_CHECK(cudaMemcpyAsync(&sd->grad[sd->nownpoints][0][0], E.d_grad + (size_t)(d->rowbase + d->sch.ghost_row0) * CFDP_DIM2,
+                                 nadd * CFDP_DIM2 * sizeof(double), cudaMemcpyDeviceToHost, R.s_d2h));
+    }
+    for (Domain *d : E.doms)
+      if (d->cd->ndomains > 1) { d->cd->send_stage++; d->cd->recv_stage++; d->cd->comm_stage++; }
+  }
+  CUDA_CHECK(cudaEventRecord(R.ev_end, R.s_d2h));
+  CUDA_CHECK(cudaStreamWaitEvent(E.s_comp, R.ev_end, 0));
+}
+
 extern "C" double cfdp_step_e2e(int variant)
 {
   Engine &E = g_eng;
   cfdp_commit();
   CUDA_CHECK(cudaEventRecord(E.ev_t0, E.s_comp));
-  for (Domain *d : E.doms) cfdp_var_to_device(d->sd);
-  run_iteration(variant);
-  for (Domain *d : E.doms) cfdp_grad_to_host(d->sd);
+  enqueue_step_e2e(variant);
   CUDA_CHECK(cudaEventRecord(E.ev_t1, E.s_comp));
   CUDA_CHECK(cudaEventSynchronize(E.ev_t1));
   float ms = 0;
@@ -900,10 +1004,12 @@ static void gradients_entry(comm_data *cd, solver_data *sd, int variant, int fin
     /* several hosted domains advance together: the call for the first hosted domain drives all */
     if (d != E.doms[0]) return;
   }
-  if (!E.resident) for (Domain *x : E.doms) cfdp_var_to_device(x->sd);
-  run_iteration(cd->ndomains == 1 ? CFDP_COMM_FREE : variant);
   (void)final;
-  if (!E.resident) for (Domain *x : E.doms) cfdp_grad_to_host(x->sd);
+  const int v = cd->ndomains == 1 ? CFDP_COMM_FREE : variant;
+  if (E.resident) { run_iteration(v); return; }
+  /* host buffers in, host buffers out (the reference's convention); returns when sd->grad is complete */
+  enqueue_step_e2e(v);
+  CUDA_CHECK(cudaStreamSynchronize(E.s_comp));
 }
 
 extern "C" void compute_gradients_gg_comm_free(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_COMM_FREE, final); }
@@ -1065,6 +1171,7 @@ extern "C" void cfdp_finalize(void)
   E.doms.clear(); E.d_rowmap.clear(); E.point_of_row.clear(); E.peers.clear(); E.send_rows_of.clear(); E.recv_rows_of.clear();
   if (E.pipe.prof) { cudaFree(E.pipe.prof); E.pipe.prof = nullptr; }
   if (E.d_progress) { cudaFree(E.d_progress); E.d_progress = nullptr; }
+  e2e_release();
 
   E.d_var = E.d_grad = E.d_pvol = nullptr; E.d_blob = nullptr; E.d_tiles = nullptr; E.d_stage = nullptr;
   E.d_loc_dst = E.d_loc_src = E.d_send_rows = E.d_recv_rows = nullptr; E.d_sendbuf = E.d_recvbuf = nullptr;

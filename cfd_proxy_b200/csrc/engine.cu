@@ -115,8 +115,10 @@ struct Engine {
   TileDesc *d_tiles = nullptr;
   size_t blob_bytes = 0;
   int smem_bytes = 0, region0_doubles = 0, block_threads = 0;
-  int kernel_version = 2, chunk = 16, smem_v1 = 0; ggk::PipeLayout pipe = {0, 256, nullptr, nullptr, 0};
+  int kernel_version = 2, chunk = 16, smem_v1 = 0; ggk::PipeLayout pipe = {0, 256, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr};
   unsigned long long *d_progress = nullptr; unsigned long long progress_target = 0; int fused_signal = 1;
+  /* fused pack: per boundary tile, the rows other domains need (export lists), written by the gradient kernel itself */
+  std::vector<uint32_t> h_exp_off, h_exp_src, h_exp_dst; uint32_t *d_exp_off = nullptr, *d_exp_src = nullptr, *d_exp_dst = nullptr; int fused_pack = 1;
   /* one-sided exchange: double-buffered receive window + per-peer arrival counters (exchange_data_gaspi.c:105-151) */
   bool ipc_ready = false; double *d_recvwin = nullptr; unsigned long long *d_arrived = nullptr; unsigned long long ipc_stage = 0; uint32_t max_footprint = 0;
   size_t max_blob = 0; int max_nhalo = 0;
@@ -230,7 +232,7 @@ extern "C" int cfdp_configure(int proc_rank, int nprocs, int ndomains_total, int
   E.sopt.bank_placement = env_int("CFDP_BANK_PLACEMENT", 1);
   E.sopt.slack_slots = env_int("CFDP_SLACK_SLOTS", 0);
   E.sopt.slack_halo = env_int("CFDP_SLACK_HALO", 0);
-  E.sopt.stage_budget = env_int("CFDP_STAGE_BUDGET", 105 * 1024); /* two tiles (two CTAs or two stages) in 228 KB of shared memory per SM */
+  E.sopt.stage_budget = env_int("CFDP_STAGE_BUDGET", 104 * 1024); /* two tiles (two CTAs or two stages) in 228 KB of shared memory per SM */
   E.exact = env_int("CFDP_EXACT", 1);
   E.configured = true;
   return 0;
@@ -374,11 +376,14 @@ static void launch_rows_copy(double *dst, const uint32_t *dst_rows, const double
   g_eng.launches++;
 }
 
-static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st, int nsignal = 0)
+static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st, int nsignal = 0, bool exports = false)
 {
   Engine &E = g_eng;
   if (ntiles <= 0) return;
   E.pipe.nsignal = nsignal; E.pipe.progress = E.d_progress;
+  E.pipe.tile_base = (int)tile0;
+  E.pipe.nexport = (exports && E.fused_pack && E.kernel_version == 2) ? (int)E.nbtiles : 0;
+  E.pipe.exp_off = E.d_exp_off; E.pipe.exp_src = E.d_exp_src; E.pipe.exp_dst = E.d_exp_dst; E.pipe.sendbuf = E.d_sendbuf;
   if (E.kernel_version == 2) {
     const unsigned grid = (unsigned)((ntiles + E.chunk - 1) / E.chunk);
     if (E.exact)
@@ -515,6 +520,38 @@ extern "C" void cfdp_plan(void)
     E.peers.push_back(pp);
   }
   E.n_send = (long long)E.h_send_rows.size(); E.n_recv = (long long)E.h_recv_rows.size();
+
+  /* 4. export lists (fused pack, threads.c:187-249 "pack while computing"): for every boundary tile the rows of it
+   * that some other domain needs, with their destination: a ghost row of a domain hosted on this GPU (bit 31
+   * clear, row of grad) or a slot of the packed send buffer (bit 31 set) */
+  {
+    std::vector<std::pair<uint32_t, int>> by_row((size_t)E.ntiles);
+    for (long long t = 0; t < E.ntiles; t++) by_row[(size_t)t] = {E.h_tiles[(size_t)t].row0, (int)t};
+    std::sort(by_row.begin(), by_row.end());
+    auto tile_of = [&](uint32_t row) {
+      auto it = std::upper_bound(by_row.begin(), by_row.end(), std::make_pair(row, 0x7FFFFFFF));
+      ASSERT(it != by_row.begin());
+      --it;
+      const TileDesc &td = E.h_tiles[(size_t)it->second];
+      ASSERT(row >= td.row0 && row < td.row0 + td.npts);
+      return it->second;
+    };
+    const size_t nexp = E.h_loc_src.size() + E.h_send_rows.size();
+    std::vector<int> etile(nexp); std::vector<uint32_t> esrc(nexp), edst(nexp);
+    size_t n = 0;
+    for (size_t i = 0; i < E.h_loc_src.size(); i++, n++) { etile[n] = tile_of(E.h_loc_src[i]); esrc[n] = E.h_loc_src[i]; edst[n] = E.h_loc_dst[i]; }
+    for (size_t i = 0; i < E.h_send_rows.size(); i++, n++) { etile[n] = tile_of(E.h_send_rows[i]); esrc[n] = E.h_send_rows[i]; edst[n] = (uint32_t)i | 0x80000000u; }
+    E.h_exp_off.assign((size_t)E.nbtiles + 1, 0);
+    for (size_t i = 0; i < nexp; i++) { ASSERT(etile[i] < E.nbtiles); E.h_exp_off[(size_t)etile[i] + 1]++; } /* send points live in boundary tiles */
+    for (long long t = 0; t < E.nbtiles; t++) E.h_exp_off[(size_t)t + 1] += E.h_exp_off[(size_t)t];
+    E.h_exp_src.resize(nexp); E.h_exp_dst.resize(nexp);
+    std::vector<uint32_t> cur(E.h_exp_off.begin(), E.h_exp_off.end() - 1);
+    for (size_t i = 0; i < nexp; i++) {
+      const uint32_t pos = cur[(size_t)etile[i]]++;
+      E.h_exp_src[pos] = esrc[i] - E.h_tiles[(size_t)etile[i]].row0;   /* tile-local point */
+      E.h_exp_dst[pos] = edst[i];
+    }
+  }
   E.planned = true;
 }
 
@@ -585,6 +622,8 @@ extern "C" void cfdp_commit(void)
   }
 
   E.d_loc_dst = upload(E.h_loc_dst); E.d_loc_src = upload(E.h_loc_src);
+  E.d_exp_off = upload(E.h_exp_off); E.d_exp_src = upload(E.h_exp_src); E.d_exp_dst = upload(E.h_exp_dst);
+  E.fused_pack = env_int("CFDP_FUSED_PACK", 1);
   E.d_send_rows = upload(E.h_send_rows); E.d_recv_rows = upload(E.h_recv_rows);
   CUDA_CHECK(cudaMalloc(&E.d_sendbuf, (size_t)std::max<long long>(E.n_send, 1) * CFDP_DIM2 * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&E.d_recvbuf, (size_t)std::max<long long>(E.n_recv, 1) * CFDP_DIM2 * sizeof(double)));
@@ -699,14 +738,14 @@ static void ipc_setup(void)
 
 static CUresult stream_wait_geq(cudaStream_t st, const void *addr, unsigned long long value);
 
-static void enqueue_exchange_onesided(cudaStream_t st)
+static void enqueue_exchange_onesided(cudaStream_t st, bool packed)
 {
   Engine &E = g_eng;
-  launch_rows_copy(E.d_grad, E.d_loc_dst, E.d_grad, E.d_loc_src, E.n_local, CFDP_DIM2, st);
+  if (!packed) launch_rows_copy(E.d_grad, E.d_loc_dst, E.d_grad, E.d_loc_src, E.n_local, CFDP_DIM2, st);
   if (E.peers.empty()) return;
   const unsigned long long stage = E.ipc_stage++;
   const int half = (int)(stage & 1);                                                               /* exchange_data_gaspi.c:181 */
-  launch_rows_copy(E.d_sendbuf, nullptr, E.d_grad, E.d_send_rows, E.n_send, CFDP_DIM2, st);      /* threads.c:791-813 */
+  if (!packed) launch_rows_copy(E.d_sendbuf, nullptr, E.d_grad, E.d_send_rows, E.n_send, CFDP_DIM2, st);      /* threads.c:791-813 */
   for (const PeerPlan &p : E.peers) {
     if (!p.send_rows) continue;
     double *dst = p.peer_recvbuf + ((size_t)half * (size_t)p.remote_recv_total + (size_t)p.remote_recv_off) * CFDP_DIM2;
@@ -724,13 +763,13 @@ static void enqueue_exchange_onesided(cudaStream_t st)
   launch_rows_copy(E.d_grad, E.d_recv_rows, E.d_recvwin + (size_t)half * (size_t)E.n_recv * CFDP_DIM2, nullptr, E.n_recv, CFDP_DIM2, st);
 }
 
-static void enqueue_exchange(cudaStream_t st)
+static void enqueue_exchange(cudaStream_t st, bool packed)
 {
   Engine &E = g_eng;
   /* halo rows whose owner lives on this GPU: one gather/scatter, no staging */
-  launch_rows_copy(E.d_grad, E.d_loc_dst, E.d_grad, E.d_loc_src, E.n_local, CFDP_DIM2, st);
+  if (!packed) launch_rows_copy(E.d_grad, E.d_loc_dst, E.d_grad, E.d_loc_src, E.n_local, CFDP_DIM2, st);
   if (E.peers.empty()) return;
-  launch_rows_copy(E.d_sendbuf, nullptr, E.d_grad, E.d_send_rows, E.n_send, CFDP_DIM2, st);      /* threads.c:791-813 */
+  if (!packed) launch_rows_copy(E.d_sendbuf, nullptr, E.d_grad, E.d_send_rows, E.n_send, CFDP_DIM2, st);      /* threads.c:791-813 */
   NCCL_CHECK(g_nccl.GroupStart());
   for (const PeerPlan &p : E.peers) {                                                               /* exchange_data_mpi.c:96-166 */
     if (p.recv_rows) NCCL_CHECK(g_nccl.Recv(E.d_recvbuf + p.recv_off * CFDP_DIM2, (size_t)p.recv_rows * CFDP_DIM2, NCCL_FLOAT64, p.proc, E.comm, st));
@@ -762,12 +801,14 @@ static CUresult stream_wait_geq(cudaStream_t st, const void *addr, unsigned long
   return fn((CUstream)st, (CUdeviceptr)addr, (cuuint64_t)value, CU_STREAM_WAIT_VALUE_GEQ);
 }
 
-static void enqueue_exchange_for(int variant, cudaStream_t st)
+/* packed: the gradient kernel already wrote the send buffer and the ghost rows of same-GPU partners (export lists) */
+static void enqueue_exchange_for(int variant, cudaStream_t st, bool packed)
 {
   Engine &E = g_eng;
   const bool onesided = (variant == CFDP_GASPI_BULK_SYNC || variant == CFDP_GASPI_ASYNC) && E.ipc_ready && get_wait_value64();
-  if (onesided) enqueue_exchange_onesided(st); else enqueue_exchange(st);
+  if (onesided) enqueue_exchange_onesided(st, packed); else enqueue_exchange(st, packed);
 }
+static bool kernel_packs(void) { return g_eng.fused_pack && g_eng.kernel_version == 2; }
 
 static void run_iteration(int variant)
 {
@@ -776,9 +817,9 @@ static void run_iteration(int variant)
   if (variant == CFDP_COMM_FREE || !have_exchange()) {
     launch_gradient(0, E.ntiles, E.s_comp);                       /* gradients.c:150-165 */
   } else if (!overlap) {
-    launch_gradient(0, E.ntiles, E.s_comp);                       /* bulk synchronous: compute, then exchange (exchange_data_mpi.c:199-284) */
+    launch_gradient(0, E.ntiles, E.s_comp, 0, true);              /* bulk synchronous: compute (packing on the way, threads.c:187-249), then exchange (exchange_data_mpi.c:199-284) */
     if (E.timeline_ek) CUDA_CHECK(cudaEventRecord(E.timeline_ek, E.s_comp));
-    enqueue_exchange_for(variant, E.s_comp);
+    enqueue_exchange_for(variant, E.s_comp, kernel_packs());
     if (E.timeline_ex) CUDA_CHECK(cudaEventRecord(E.timeline_ex, E.s_comp));
   } else {
     /* early send (threads.c:253-346): tiles holding send points first, their rows are packed and
@@ -788,11 +829,11 @@ static void run_iteration(int variant)
       /* ONE launch over all tiles; every retired boundary tile bumps a device counter and the comm stream
        * sleeps on the counter (stream memory operation) -- no split launch, no tail between the two parts */
       E.progress_target += (unsigned long long)E.nbtiles;
-      launch_gradient(0, E.ntiles, E.s_comp, (int)E.nbtiles);
+      launch_gradient(0, E.ntiles, E.s_comp, (int)E.nbtiles, true);
       CUresult r = wait64((CUstream)E.s_comm, (CUdeviceptr)E.d_progress, (cuuint64_t)E.progress_target, CU_STREAM_WAIT_VALUE_GEQ);
       ASSERT(r == CUDA_SUCCESS);
       if (E.timeline_ek) CUDA_CHECK(cudaEventRecord(E.timeline_ek, E.s_comp));
-      enqueue_exchange_for(variant, E.s_comm);
+      enqueue_exchange_for(variant, E.s_comm, kernel_packs());
       if (E.timeline_ex) CUDA_CHECK(cudaEventRecord(E.timeline_ex, E.s_comm));
       CUDA_CHECK(cudaEventRecord(E.ev_x, E.s_comm));
       CUDA_CHECK(cudaStreamWaitEvent(E.s_comp, E.ev_x, 0));
@@ -800,10 +841,10 @@ static void run_iteration(int variant)
         if (d->cd->ndomains > 1) { d->cd->send_stage++; d->cd->recv_stage++; d->cd->comm_stage++; }
       return;
     }
-    launch_gradient(0, E.nbtiles, E.s_comp);
+    launch_gradient(0, E.nbtiles, E.s_comp, 0, true);
     CUDA_CHECK(cudaEventRecord(E.ev_b, E.s_comp));
     CUDA_CHECK(cudaStreamWaitEvent(E.s_comm, E.ev_b, 0));
-    enqueue_exchange_for(variant, E.s_comm);
+    enqueue_exchange_for(variant, E.s_comm, kernel_packs());
     if (E.timeline_ex) CUDA_CHECK(cudaEventRecord(E.timeline_ex, E.s_comm));
     CUDA_CHECK(cudaEventRecord(E.ev_x, E.s_comm));
     launch_gradient(E.nbtiles, E.ntiles - E.nbtiles, E.s_comp);
@@ -928,7 +969,7 @@ static void enqueue_step_e2e(int variant)
     CUDA_CHECK(cudaStreamWaitEvent(E.s_comp, R.ev_up[b], 0));
     launch_rows_copy(E.d_var, (const uint32_t *)E.d_rowmap[(size_t)i], R.var_stage[b], nullptr, (long long)nall, NGRAD, E.s_comp, 0.5);
     CUDA_CHECK(cudaEventRecord(R.ev_var_free[b], E.s_comp));
-    launch_gradient(d->tile0_b, d->sch.nboundary, E.s_comp);
+    launch_gradient(d->tile0_b, d->sch.nboundary, E.s_comp, 0, exchange);
     launch_gradient(d->tile0_i, d->sch.ntiles - d->sch.nboundary, E.s_comp);
     /* down: own rows back in host order */
     if (i >= 2) CUDA_CHECK(cudaStreamWaitEvent(E.s_comp, R.ev_grad_free[b], 0));
@@ -940,7 +981,7 @@ static void enqueue_step_e2e(int variant)
   }
   if (exchange) {
     /* every domain's rows are final: halo exchange, then the ghost rows (contiguous on both sides) */
-    enqueue_exchange_for(variant, E.s_comp);
+    enqueue_exchange_for(variant, E.s_comp, kernel_packs());
     CUDA_CHECK(cudaEventRecord(R.ev_x, E.s_comp));
     CUDA_CHECK(cudaStreamWaitEvent(R.s_d2h, R.ev_x, 0));
     for (int i = 0; i < nh; i++) {
@@ -1143,7 +1184,7 @@ extern "C" void cfdp_finalize(void)
     cudaDeviceSynchronize();
     if (E.comm) { g_nccl.CommDestroy(E.comm); E.comm = nullptr; }
     cudaFree(E.d_var); cudaFree(E.d_grad); cudaFree(E.d_pvol); cudaFree(E.d_blob); cudaFree(E.d_tiles); cudaFree(E.d_stage);
-    cudaFree(E.d_loc_dst); cudaFree(E.d_loc_src); cudaFree(E.d_send_rows); cudaFree(E.d_recv_rows); cudaFree(E.d_sendbuf); cudaFree(E.d_recvbuf);
+    cudaFree(E.d_loc_dst); cudaFree(E.d_loc_src); cudaFree(E.d_exp_off); cudaFree(E.d_exp_src); cudaFree(E.d_exp_dst); cudaFree(E.d_send_rows); cudaFree(E.d_recv_rows); cudaFree(E.d_sendbuf); cudaFree(E.d_recvbuf);
     for (int *p : E.d_rowmap) cudaFree(p);
   }
   if (E.ipc_ready) {
@@ -1176,6 +1217,7 @@ extern "C" void cfdp_finalize(void)
   E.d_var = E.d_grad = E.d_pvol = nullptr; E.d_blob = nullptr; E.d_tiles = nullptr; E.d_stage = nullptr;
   E.d_loc_dst = E.d_loc_src = E.d_send_rows = E.d_recv_rows = nullptr; E.d_sendbuf = E.d_recvbuf = nullptr;
   E.committed = false; E.planned = false; E.configured = false;
+  E.h_exp_off.clear(); E.h_exp_src.clear(); E.h_exp_dst.clear(); E.d_exp_off = E.d_exp_src = E.d_exp_dst = nullptr;
   E.h_tiles.clear(); E.blob_base.clear(); E.h_loc_dst.clear(); E.h_loc_src.clear(); E.h_send_rows.clear(); E.h_recv_rows.clear();
   E.max_nfaces = E.max_nloc = E.max_npts = 0; E.max_stage = 0; E.blob_bytes = 0; E.max_blob = 0; E.max_nhalo = 0; E.max_footprint = 0;
   E.rows = E.ntiles = E.nbtiles = 0; E.nfaces = E.nown = E.nall = E.tile_faces = E.halo_refs = E.alg_bytes = 0;

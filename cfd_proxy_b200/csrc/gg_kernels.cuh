@@ -30,6 +30,7 @@
 
 #define CFDP_MAX_HALO_POS 1024  /* halo positions of a tile (shared-memory index list of the prefetcher) */
 #define CFDP_MAX_CHUNK 64      /* tiles per CTA */
+#define CFDP_MAX_EXPORT 256    /* export rows of a tile kept in shared memory (longer lists are read from global memory) */
 
 namespace ggk {
 
@@ -84,6 +85,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 __device__ __forceinline__ void cp_async8(void *dst, const void *src)
 {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
@@ -168,6 +173,10 @@ struct PipeLayout {
   unsigned long long *prof; /* optional: SM cycles of thread 0 summed over tiles: [0] wait for data, [1] face walk, [2] rest of the tile, [4] tiles */
   unsigned long long *progress; /* counts finished boundary tiles (tile index < nsignal): the early-send trigger the comm stream waits on */
   int nsignal;
+  int tile_base;  /* global index of this launch's first tile */
+  int nexport;    /* global tiles [0, nexport) write their export rows (fused pack); 0 = off */
+  const uint32_t *exp_off, *exp_src, *exp_dst; /* per boundary tile: tile-local point -> grad row (bit 31 clear) or send-buffer slot (bit 31 set) */
+  double *sendbuf;
 };
 
 __device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes, uint64_t policy)
@@ -207,6 +216,8 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
   __shared__ uint64_t full;
   __shared__ TileDesc s_tds[CFDP_MAX_CHUNK];   /* descriptors of this CTA's tiles */
   __shared__ __align__(16) uint32_t s_hidx[CFDP_MAX_HALO_POS]; /* halo row list of the tile being prefetched */
+  __shared__ uint32_t s_exp[2 * CFDP_MAX_EXPORT];               /* this tile's export list: sources, then destinations */
+  __shared__ uint32_t s_exp_off[CFDP_MAX_CHUNK + 1];            /* export list bounds of this CTA's tiles */
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int t_begin = blockIdx.x * chunk;
   const int t_end = min(t_begin + chunk, ntiles);
@@ -216,6 +227,10 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     const uint32_t *g = reinterpret_cast<const uint32_t *>(tiles + t_begin);
     uint32_t *d = reinterpret_cast<uint32_t *>(s_tds);
     for (int i = tid; i < nw; i += nthr) d[i] = __ldg(g + i);
+    for (int i = tid; i <= t_end - t_begin; i += nthr) {
+      const int gt = L.tile_base + t_begin + i;
+      s_exp_off[i] = gt <= L.nexport ? __ldg(L.exp_off + gt) : 0u; /* exp_off has nexport + 1 entries */
+    }
   }
   if (tid == 0) {
     mbar_init(&full, (uint32_t)nthr + 1);
@@ -308,16 +323,44 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
         gather_halo(nd);
       }
     }
+    /* export list of this tile (fused pack), fetched asynchronously while the rows are being staged */
+    const int gt = L.tile_base + t;
+    const uint32_t e0 = gt < L.nexport ? s_exp_off[t - t_begin] : 0u;
+    const int nexp = gt < L.nexport ? (int)(s_exp_off[t - t_begin + 1] - e0) : 0;
+    const bool exp_in_smem = nexp > 0 && nexp <= CFDP_MAX_EXPORT;
+    if (exp_in_smem) {
+      for (int i = tid; i < nexp; i += nthr) {
+        cp_async4(&s_exp[i], L.exp_src + e0 + i);
+        cp_async4(&s_exp[CFDP_MAX_EXPORT + i], L.exp_dst + e0 + i);
+      }
+      cp_async_commit();
+    }
     if (active) {
       double *o = s_nrm + tid * (NGRAD * 3);
 #pragma unroll
       for (int k = 0; k < NGRAD * 3; k++) o[k] = acc[k];
     }
     fence_proxy_async(); /* the staged rows (generic proxy) become visible to the bulk store (async proxy) */
+    cp_async_wait_all(); /* export list */
     __syncthreads();     /* S2 */
     if (tid == 0) {
       bulk_s2g(grad + (size_t)td.row0 * (NGRAD * 3), s_nrm, out_rows * (NGRAD * 3 * 8), pol_stream); /* rows beyond npts are alignment padding */
       bulk_commit();
+    }
+    if (nexp > 0) {
+      /* fused pack (threads.c:187-249, :791-813): the rows of this tile that other domains need go straight from the
+       * staged rows to the packed send buffer, or to the ghost rows of a domain hosted on this GPU */
+      const int nw = nexp * (NGRAD * 3);
+      for (int i = tid; i < nw; i += nthr) {
+        const int r = i / (NGRAD * 3), c = i - r * (NGRAD * 3);
+        const uint32_t src = exp_in_smem ? s_exp[r] : __ldg(L.exp_src + e0 + r);
+        const uint32_t dst = exp_in_smem ? s_exp[CFDP_MAX_EXPORT + r] : __ldg(L.exp_dst + e0 + r);
+        double *base = (dst & 0x80000000u) ? L.sendbuf : grad;
+        base[(size_t)(dst & 0x7FFFFFFFu) * (NGRAD * 3) + c] = s_nrm[src * (NGRAD * 3) + c];
+      }
+      __syncthreads(); /* the staged rows have been read by every thread (and ordered before thread 0's release below) */
+    }
+    if (tid == 0) {
       bulk_wait_read();      /* shared memory may be overwritten */
       /* boundary tiles: their rows may be packed / copied by the exchange as soon as every boundary tile has retired
        * (the reference's finalised-send-point counters, threads.c:268-306).  A CTA reports its boundary tiles in

@@ -288,7 +288,6 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
   int pending_sig = 0; /* thread 0: boundary tiles stored but not yet signalled */
   for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
     const bool has_next = t + 1 < t_end;
-    stage_pf_index(t + 1); /* lands during the face walk */
     const TileDesc td = s_tds[t - t_begin];
     const int npts = td.npts, nhalo = td.nhalo;
     double *s_nrm = reinterpret_cast<double *>(st);
@@ -299,6 +298,9 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     if (L.prof && tid == 0) c0 = clock64();
     mbar_wait(&full, (uint32_t)it & 1u);
     if (L.prof && tid == 0) c1 = clock64();
+    /* the phase completes only after every thread has arrived, i.e. is done reading s_hidx for this tile's halo
+     * gather: the list of the next tile may now be fetched; it lands during the face walk */
+    stage_pf_index(t + 1);
 
     double acc[NGRAD * 3];
     const bool active = tid < npts;
@@ -310,7 +312,8 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     __syncthreads();     /* S1: normals, adjacency and var of this tile are dead */
     if (L.prof && tid == 0) c2 = clock64();
 
-    /* the output rows are staged in [0, out_end); whatever of the next tile lives beyond can be fetched now */
+    /* the output rows are staged in [0, out_end) and leave through one bulk store; while the TMA engine reads them,
+     * whatever of the next tile lives beyond out_end is fetched; the head of its blob follows when the read is done */
     const uint32_t out_rows = CFDP_HALO_BASE((uint32_t)npts);
     const uint32_t out_end = (out_rows * (NGRAD * 3 * 8) + 127u) & ~127u;
     TileDesc nd = td;
@@ -318,10 +321,6 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     if (has_next) {
       nd = s_tds[t + 1 - t_begin];
       early = tile_var_off(nd.blob_bytes, nd.npts) >= out_end;
-      if (early) {
-        if (tid == 0) bulk_part(nd, out_end < nd.blob_bytes ? out_end : nd.blob_bytes, nd.blob_bytes, true, true);
-        gather_halo(nd);
-      }
     }
     /* export list of this tile (fused pack), fetched asynchronously while the rows are being staged */
     const int gt = L.tile_base + t;
@@ -343,6 +342,8 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     fence_proxy_async(); /* the staged rows (generic proxy) become visible to the bulk store (async proxy) */
     cp_async_wait_all(); /* export list */
     __syncthreads();     /* S2 */
+    long long q1 = 0, q2 = 0, q3 = 0;
+    if (L.prof && tid == 0) q1 = clock64();
     if (tid == 0) {
       bulk_s2g(grad + (size_t)td.row0 * (NGRAD * 3), s_nrm, out_rows * (NGRAD * 3 * 8), pol_stream); /* rows beyond npts are alignment padding */
       bulk_commit();
@@ -360,8 +361,14 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
       }
       __syncthreads(); /* the staged rows have been read by every thread (and ordered before thread 0's release below) */
     }
+    if (has_next && early) { /* runs while the bulk store drains the staged rows */
+      if (tid == 0) bulk_part(nd, out_end < nd.blob_bytes ? out_end : nd.blob_bytes, nd.blob_bytes, true, true);
+      gather_halo(nd);
+    }
+    if (L.prof && tid == 0) q2 = clock64();
     if (tid == 0) {
       bulk_wait_read();      /* shared memory may be overwritten */
+      if (L.prof) q3 = clock64();
       /* boundary tiles: their rows may be packed / copied by the exchange as soon as every boundary tile has retired
        * (the reference's finalised-send-point counters, threads.c:268-306).  A CTA reports its boundary tiles in
        * one go, when it retires or reaches its first interior tile: nobody waits for a write to reach global memory. */
@@ -385,6 +392,8 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
       const long long c3 = clock64();
       atomicAdd(L.prof + 0, (unsigned long long)(c1 - c0)); atomicAdd(L.prof + 1, (unsigned long long)(c2 - c1));
       atomicAdd(L.prof + 2, (unsigned long long)(c3 - c2)); atomicAdd(L.prof + 4, 1ull);
+      atomicAdd(L.prof + 5, (unsigned long long)(q1 - c2)); atomicAdd(L.prof + 6, (unsigned long long)(q2 - q1)); atomicAdd(L.prof + 7, (unsigned long long)(q3 - q2));
+      /* [5] staging up to S2, [6] store issue + exports + early fetch, [7] wait for the store to have read shared memory */
     }
   }
   if (tid == 0 && pending_sig) {

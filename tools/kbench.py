@@ -45,7 +45,7 @@ def main():
                 S.iterate("comm_free", 5)
                 S.lib.cfdp_get_phase_profile(buf, 1)
                 nt = max(buf[4], 1)
-                prof = dict(wait=round(buf[0] / nt), walk=round(buf[1] / nt), rest=round(buf[2] / nt))
+                prof = dict(wait=round(buf[0] / nt), walk=round(buf[1] / nt), rest=round(buf[2] / nt), stage_S2=round(buf[5] / nt), store_exports_earlyfetch=round(buf[6] / nt), wait_read=round(buf[7] / nt))
                 print("  phase cycles per tile (thread 0):", prof, flush=True)
             print(json.dumps(dict(cfg=cfg, kernel_ms=round(ms, 4), gfaces=round(st.nfaces / ms / 1e6, 2), frac=round(st.alg_bytes / ms / 1e6 / peak, 4),
                                   async_ms=round(ms_a, 4), smem=st.smem_bytes, tiles=st.ntiles, dup=round(st.tile_faces / st.nfaces, 3),

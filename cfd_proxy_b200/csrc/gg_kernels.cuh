@@ -196,15 +196,16 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 /*
  * Two CTAs per SM, each owning one shared-memory stage and a chunk of consecutive tiles.  Timeline of a tile t:
- *   wait(mbarrier)            all of tile t has landed (bulk copies + halo gather)
+ *   wait(mbarrier)            all of tile t has landed (bulk copies + halo gather); then the halo row list of tile
+ *                             t+1 is prefetched (16-byte cp.async) and lands during the walk
  *   face walk                 one thread per point, 21 sums in registers
  *   S1 barrier                normals / adjacency / var of tile t are dead
- *   early fetch of tile t+1   var rows, volumes, blob tail (bulk copies) and the halo gather (8-byte cp.async): everything
- *                             that does not overlap the output staging of tile t
  *   stage the rows of tile t  into the head of the stage (transposed through shared memory)
  *   S2 barrier
- *   TMA bulk store of the rows (one instruction), wait until shared memory has been read, then the head of tile
- *   t+1's blob.  While this CTA waits, the other CTA of the SM computes.
+ *   TMA bulk store of the rows (one instruction); boundary tiles also write their export rows (fused pack)
+ *   early fetch of tile t+1   while the TMA engine drains the staged rows: var rows, volumes, blob tail (bulk copies)
+ *                             and the halo gather (8-byte cp.async): everything that does not overlap the staged rows
+ *   head of tile t+1's blob   once the store has read shared memory.  While this CTA waits, the other CTA computes.
  * No thread ever blocks on a global load: HBM is touched only by asynchronous copies.
  */
 template <bool EXACT>

@@ -1177,6 +1177,33 @@ extern "C" int cfdp_get_exchange_entry(int dir, long long j, int *domain, int *p
   return -1;
 }
 
+extern "C" int cfdp_get_row_owner(long long row, int *domain, int *point)
+{
+  Engine &E = g_eng;
+  if (!E.planned) return -1;
+  for (size_t i = 0; i < E.doms.size(); i++) {
+    Domain *d = E.doms[i];
+    if (row >= d->rowbase && row < d->rowbase + d->sch.nrows) {
+      *domain = d->id; *point = E.point_of_row[i][(size_t)(row - d->rowbase)];
+      return *point >= 0 ? 0 : -1;
+    }
+  }
+  return -1;
+}
+
+extern "C" int cfdp_get_tile_exports(int tile, int capacity, unsigned *src_row, unsigned *dst, int *kind)
+{
+  Engine &E = g_eng;
+  if (!E.planned || tile < 0 || tile >= E.nbtiles) return -1;
+  const uint32_t e0 = E.h_exp_off[(size_t)tile], e1 = E.h_exp_off[(size_t)tile + 1];
+  for (uint32_t e = e0; e < e1 && (int)(e - e0) < capacity; e++) {
+    if (src_row) src_row[e - e0] = E.h_tiles[(size_t)tile].row0 + E.h_exp_src[e];
+    if (dst) dst[e - e0] = E.h_exp_dst[e] & 0x7FFFFFFFu;
+    if (kind) kind[e - e0] = (E.h_exp_dst[e] >> 31) & 1;
+  }
+  return (int)(e1 - e0);
+}
+
 extern "C" void cfdp_finalize(void)
 {
   Engine &E = g_eng;

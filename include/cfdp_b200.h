@@ -169,6 +169,14 @@ void cfdp_set_int_exchange(cfdp_int_exchange_fn fn);
 int cfdp_get_peer_plan(int i, int *proc, long long *send_rows, long long *recv_rows);
 /* host point (domain rank, local point id) behind entry j of the packed send (dir = 0) / recv (dir = 1) buffer */
 int cfdp_get_exchange_entry(int dir, long long j, int *domain, int *point);
+/* export list of boundary tile `tile` (index in the per-GPU tile list, < nboundary_tiles): the rows the gradient kernel
+ * writes for other domains while it still holds them (fused pack).  Entry i: src_row[i] = device row inside the tile,
+ * kind[i] = 0: dst[i] is the device row of a ghost point of a domain hosted on this GPU; kind[i] = 1: dst[i] is a slot
+ * of the packed send buffer (see cfdp_get_exchange_entry(0, slot, ...)).  Returns the number of entries (arrays may
+ * be NULL), -1 on error.  The analogue of the per-colour send lists checked by thread_comm.c:159-205. */
+int cfdp_get_tile_exports(int tile, int capacity, unsigned *src_row, unsigned *dst, int *kind);
+/* device row -> (hosted domain rank, local point id); -1 when the row is alignment padding */
+int cfdp_get_row_owner(long long row, int *domain, int *point);
 /* called once after init_threads() of every hosted domain (implicit on first compute call):
  * builds the unified device layout, the pack/unpack lists and the exchange plan */
 void cfdp_commit(void);

@@ -87,6 +87,28 @@ def main():
             errors.append(f"rank {rank} -> {q}: send order does not match the peer's receive order")
         if rg != their_s:
             errors.append(f"rank {q} -> {rank}: receive order does not match the peer's send order")
+    # 3. fused pack: every slot of the packed send buffer is filled exactly once, by the tile that owns the source point
+    st0 = S.stats()
+    filled = {}
+    for t in range(st0.nboundary_tiles):
+        ne = lib.cfdp_get_tile_exports(t, 0, None, None, None)
+        src = (C.c_uint * max(ne, 1))(); dst = (C.c_uint * max(ne, 1))(); kind = (C.c_int * max(ne, 1))()
+        lib.cfdp_get_tile_exports(t, ne, src, dst, kind)
+        for i in range(ne):
+            if kind[i] != 1:
+                continue
+            sd, sp, ed, ep = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            if lib.cfdp_get_row_owner(src[i], C.byref(sd), C.byref(sp)) != 0 or \
+               lib.cfdp_get_exchange_entry(0, dst[i], C.byref(ed), C.byref(ep)) != 0:
+                errors.append("bad export entry")
+                continue
+            if dst[i] in filled:
+                errors.append(f"send slot {dst[i]} filled twice")
+            filled[dst[i]] = 1
+            if (sd.value, sp.value) != (ed.value, ep.value):
+                errors.append(f"send slot {dst[i]} filled from the wrong point")
+    if len(filled) != st0.send_rows_remote:
+        errors.append(f"{len(filled)} send slots filled, {st0.send_rows_remote} expected")
     st = S.stats()
     total_remote = sum(len(v[0]) for v in plan.values())
     if total_remote != st.send_rows_remote:

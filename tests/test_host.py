@@ -245,3 +245,38 @@ def test_mesh_generator_invariants():
     lib = L.load()
     v = M.var_for(doms[0])
     assert v[3, 2] == lib.cfdp_mesh_var_value(M.DEFAULT_SEED, int(doms[0]["global_id"][3]), 2)
+
+
+@pytest.mark.parametrize("n,p,order,hexfrac,tile", [((20, 16, 12), (2, 2, 1), "shuffle", 0.4, 64), ((24, 20, 16), (3, 2, 2), "lex", 0.25, 256)])
+def test_fused_pack_export_lists_cover_every_halo_row_once(session_factory, n, p, order, hexfrac, tile):
+    """The boundary tiles' export lists (fused pack) against the halo lists, the check the reference makes for its
+    per-colour send lists (thread_comm.c:159-205): every (ghost point of a hosted partner) is written exactly once,
+    by the tile that owns the source point, from the point cd->sendindex / cd->recvindex pair up."""
+    spec = M.make_spec(n, p, order=order, brick=4, hexfrac=hexfrac)
+    nd = p[0] * p[1] * p[2]
+    doms = [M.gen_domain(spec, r) for r in range(nd)]
+    recv, send = O.recvsend_index(doms)
+    S = session_factory(nd, tile_points=tile)
+    S.load_spec(spec)
+    S.setup(device=False)
+    lib, st = S.lib, S.stats()
+    want = {}   # (dst domain, ghost point) -> (src domain, own point)
+    for a in range(nd):
+        for k, ridx in recv[a].items():
+            for j, g in enumerate(ridx):
+                want[(a, int(g))] = (k, int(send[k][a][j]))
+    got = {}
+    for t in range(st.nboundary_tiles):
+        ne = lib.cfdp_get_tile_exports(t, 0, None, None, None)
+        src = (C.c_uint * max(ne, 1))(); dst = (C.c_uint * max(ne, 1))(); kind = (C.c_int * max(ne, 1))()
+        assert lib.cfdp_get_tile_exports(t, ne, src, dst, kind) == ne
+        for i in range(ne):
+            assert kind[i] == 0                       # one process hosts every domain: no send buffer
+            sd, sp, dd, dp = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            assert lib.cfdp_get_row_owner(src[i], C.byref(sd), C.byref(sp)) == 0
+            assert lib.cfdp_get_row_owner(dst[i], C.byref(dd), C.byref(dp)) == 0
+            key = (dd.value, dp.value)
+            assert key not in got                     # each ghost row written exactly once
+            got[key] = (sd.value, sp.value)
+    assert got == want
+    assert st.send_rows_local == len(want)

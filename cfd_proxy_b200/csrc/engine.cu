@@ -115,7 +115,7 @@ struct Engine {
   TileDesc *d_tiles = nullptr;
   size_t blob_bytes = 0;
   int smem_bytes = 0, region0_doubles = 0, block_threads = 0;
-  int kernel_version = 2, chunk = 16, smem_v1 = 0; ggk::PipeLayout pipe = {0, 256, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr};
+  int kernel_version = 2, chunk = 16, smem_v1 = 0; ggk::PipeLayout pipe = {0, 256, nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr};
   unsigned long long *d_progress = nullptr; unsigned long long progress_target = 0; int fused_signal = 1;
   /* fused pack: per boundary tile, the rows other domains need (export lists), written by the gradient kernel itself */
   std::vector<uint32_t> h_exp_off, h_exp_src, h_exp_dst; uint32_t *d_exp_off = nullptr, *d_exp_src = nullptr, *d_exp_dst = nullptr; int fused_pack = 1;
@@ -227,6 +227,12 @@ extern "C" int cfdp_configure(int proc_rank, int nprocs, int ndomains_total, int
   E.sopt.tile_points = env_int("CFDP_TILE_POINTS", 256);
   E.sopt.max_faces = env_int("CFDP_TILE_MAX_FACES", 2688);
   E.sopt.max_local = env_int("CFDP_TILE_MAX_LOCAL", 768);
+  {
+    /* threads that gather halo rows (gg_tile_pipe_kernel): all of the block, minus warp 0 for blocks of >= 128 threads */
+    const int blk = (int)align_up((size_t)E.sopt.tile_points, 32), gth = blk >= 128 ? blk - 32 : blk;
+    const int max_halo = gth * CFDP_MAX_GATHER_PER_THREAD / NGRAD;
+    E.sopt.max_local = std::min(E.sopt.max_local, E.sopt.tile_points + max_halo);
+  }
   E.sopt.order = env_int("CFDP_TILE_ORDER", 0);
   E.sopt.sort_in_tile = env_int("CFDP_SORT_IN_TILE", 1);
   E.sopt.bank_placement = env_int("CFDP_BANK_PLACEMENT", 1);
@@ -604,6 +610,7 @@ extern "C" void cfdp_commit(void)
   E.chunk = std::min(CFDP_MAX_CHUNK, std::max(1, env_int("CFDP_CHUNK", 8)));
   E.pipe.block_points = E.block_threads;
   E.fused_signal = env_int("CFDP_FUSED_SIGNAL", 1);
+  E.pipe.split_roles = env_int("CFDP_SPLIT_ROLES", 0);
   CUDA_CHECK(cudaMalloc(&E.d_progress, 64)); CUDA_CHECK(cudaMemset(E.d_progress, 0, 64)); E.progress_target = 0;
   if (env_int("CFDP_PHASE_PROF", 0)) { CUDA_CHECK(cudaMalloc(&E.pipe.prof, 8 * sizeof(unsigned long long))); CUDA_CHECK(cudaMemset(E.pipe.prof, 0, 8 * sizeof(unsigned long long))); }
   const int smem_limit = 227 * 1024 - 256;

@@ -30,6 +30,7 @@
 
 #define CFDP_MAX_HALO_POS 1024  /* halo positions of a tile (shared-memory index list of the prefetcher) */
 #define CFDP_MAX_CHUNK 64      /* tiles per CTA */
+#define CFDP_MAX_GATHER_PER_THREAD 24 /* 8-byte cp.async a thread issues per tile for the halo gather (measured safe) */
 #define CFDP_MAX_EXPORT 256    /* export rows of a tile kept in shared memory (longer lists are read from global memory) */
 
 namespace ggk {
@@ -173,6 +174,7 @@ struct PipeLayout {
   unsigned long long *prof; /* optional: SM cycles of thread 0 summed over tiles: [0] wait for data, [1] face walk, [2] rest of the tile, [4] tiles */
   unsigned long long *progress; /* counts finished boundary tiles (tile index < nsignal): the early-send trigger the comm stream waits on */
   int nsignal;
+  int split_roles; /* warp 0 drives the bulk copies instead of gathering */
   int tile_base;  /* global index of this launch's first tile */
   int nexport;    /* global tiles [0, nexport) write their export rows (fused pack); 0 = off */
   const uint32_t *exp_off, *exp_src, *exp_dst; /* per boundary tile: tile-local point -> grad row (bit 31 clear) or send-buffer slot (bit 31 set) */
@@ -264,14 +266,17 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
   /* all threads: hvar rows of the halo points, consecutive lanes = consecutive words of a row.  (Moving a row as
    * 16-byte pieces needs the halo position to share the parity of the device row; measured slower: the parity
    * constraint costs more bank conflicts in the face walk than the shorter gather saves.) */
-  auto gather_halo = [&](const TileDesc &pd) {
+  auto gather_halo = [&](const TileDesc &pd, int first, int stride) { /* first < 0: this thread only arrives */
     double *vs = reinterpret_cast<double *>(st + tile_var_off(pd.blob_bytes, pd.npts)) + (size_t)CFDP_HALO_BASE((uint32_t)pd.npts) * NGRAD;
-    const int nw = (int)pd.nhalo * NGRAD;
-    for (int i = tid; i < nw; i += nthr) {
+    const int nw = first >= 0 ? (int)pd.nhalo * NGRAD : 0;
+    for (int i = first; i < nw; i += stride) {
       const int r = i / NGRAD;
       const uint32_t row = s_hidx[r];
       if (row != 0xFFFFFFFFu) cp_async8(vs + i, hvar + (size_t)row * NGRAD + (i - r * NGRAD));
     }
+    /* the arrival is issued by whole, converged warps only: issued under divergence (lane 0 of warp 0 busy with the
+     * bulk copies, or lanes leaving the loop above at different trips) the phase was observed to complete early */
+    __syncwarp();
     cp_async_mbar_arrive_noinc(&full);
   };
 
@@ -282,9 +287,16 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
   {
     const TileDesc pd = s_tds[0];
     if (tid == 0) bulk_part(pd, 0, pd.blob_bytes, true, true);
-    gather_halo(pd);
+    gather_halo(pd, tid, nthr);
   }
   __syncthreads(); /* s_hidx may be refilled */
+  /* EXPERIMENTAL, off by default (CFDP_SPLIT_ROLES=1): warp 0 does not gather, its lane 0 drives the bulk store and
+   * the bulk copies of the next tile, so that the head of the next blob is requested the moment the store has drained
+   * the staged rows.  4 % faster (1.83 -> 1.75 ms on 16.8 M points) but NOT parity clean: together with a CTA barrier
+   * between the store and the early fetch (boundary tiles of the fused pack) own rows come out wrong intermittently;
+   * the cause is not understood yet (profiles/README.md). */
+  const bool split_roles = nthr >= 128 && L.split_roles == 1;
+  const int g_first = split_roles ? (tid >= 32 ? tid - 32 : -1) : tid, g_stride = split_roles ? nthr - 32 : nthr;
 
   int pending_sig = 0; /* thread 0: boundary tiles stored but not yet signalled */
   for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
@@ -364,7 +376,7 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     }
     if (has_next && early) { /* runs while the bulk store drains the staged rows */
       if (tid == 0) bulk_part(nd, out_end < nd.blob_bytes ? out_end : nd.blob_bytes, nd.blob_bytes, true, true);
-      gather_halo(nd);
+      gather_halo(nd, g_first, g_stride);
     }
     if (L.prof && tid == 0) q2 = clock64();
     if (tid == 0) {
@@ -386,7 +398,7 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     }
     if (has_next && !early) { /* rare (a much smaller tile follows): its var rows overlap the staged rows */
       __syncthreads();
-      gather_halo(nd);
+      gather_halo(nd, tid, nthr);
       __syncthreads();
     }
     if (L.prof && tid == 0) {

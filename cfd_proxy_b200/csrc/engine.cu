@@ -610,7 +610,7 @@ extern "C" void cfdp_commit(void)
   E.chunk = std::min(CFDP_MAX_CHUNK, std::max(1, env_int("CFDP_CHUNK", 8)));
   E.pipe.block_points = E.block_threads;
   E.fused_signal = env_int("CFDP_FUSED_SIGNAL", 1);
-  E.pipe.split_roles = env_int("CFDP_SPLIT_ROLES", 0);
+  E.pipe.split_roles = env_int("CFDP_SPLIT_ROLES", 1);
   CUDA_CHECK(cudaMalloc(&E.d_progress, 64)); CUDA_CHECK(cudaMemset(E.d_progress, 0, 64)); E.progress_target = 0;
   if (env_int("CFDP_PHASE_PROF", 0)) { CUDA_CHECK(cudaMalloc(&E.pipe.prof, 8 * sizeof(unsigned long long))); CUDA_CHECK(cudaMemset(E.pipe.prof, 0, 8 * sizeof(unsigned long long))); }
   const int smem_limit = 227 * 1024 - 256;

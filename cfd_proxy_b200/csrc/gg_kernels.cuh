@@ -268,8 +268,8 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
    * constraint costs more bank conflicts in the face walk than the shorter gather saves.) */
   auto gather_halo = [&](const TileDesc &pd, int first, int stride) { /* first < 0: this thread only arrives */
     double *vs = reinterpret_cast<double *>(st + tile_var_off(pd.blob_bytes, pd.npts)) + (size_t)CFDP_HALO_BASE((uint32_t)pd.npts) * NGRAD;
-    const int nw = first >= 0 ? (int)pd.nhalo * NGRAD : 0;
-    for (int i = first; i < nw; i += stride) {
+    const int nw = (int)pd.nhalo * NGRAD;
+    for (int i = first >= 0 ? first : nw; i < nw; i += stride) {
       const int r = i / NGRAD;
       const uint32_t row = s_hidx[r];
       if (row != 0xFFFFFFFFu) cp_async8(vs + i, hvar + (size_t)row * NGRAD + (i - r * NGRAD));
@@ -290,11 +290,9 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, c
     gather_halo(pd, tid, nthr);
   }
   __syncthreads(); /* s_hidx may be refilled */
-  /* EXPERIMENTAL, off by default (CFDP_SPLIT_ROLES=1): warp 0 does not gather, its lane 0 drives the bulk store and
-   * the bulk copies of the next tile, so that the head of the next blob is requested the moment the store has drained
-   * the staged rows.  4 % faster (1.83 -> 1.75 ms on 16.8 M points) but NOT parity clean: together with a CTA barrier
-   * between the store and the early fetch (boundary tiles of the fused pack) own rows come out wrong intermittently;
-   * the cause is not understood yet (profiles/README.md). */
+  /* split roles (CFDP_SPLIT_ROLES=0 turns it off): warp 0 does not gather, its lane 0 drives the bulk store and the
+   * bulk copies of the next tile, so that the head of the next blob is requested the moment the store has drained
+   * the staged rows (4 % faster: 1.82 -> 1.75 ms on 16.8 M points) */
   const bool split_roles = nthr >= 128 && L.split_roles == 1;
   const int g_first = split_roles ? (tid >= 32 ? tid - 32 : -1) : tid, g_stride = split_roles ? nthr - 32 : nthr;
 

@@ -31,6 +31,7 @@
 #include <omp.h>
 #include "common.h"
 #include "gg_kernels.cuh"
+#include "flux_kernels.cuh"
 
 #define CUDA_CHECK(call)                                                                           \
   do {                                                                                             \
@@ -111,6 +112,7 @@ struct Engine {
   /* device */
   long long rows = 0, ntiles = 0, nbtiles = 0;
   double *d_var = nullptr, *d_grad = nullptr, *d_pvol = nullptr;
+  double *d_flux = nullptr; int with_flux = 0; uint32_t flux_smem = 0; double last_flux_ms = 0; long long flux_alg_bytes = 0; /* pseudo flux (flux.c), lazily allocated */
   unsigned char *d_blob = nullptr;
   TileDesc *d_tiles = nullptr;
   size_t blob_bytes = 0;
@@ -406,6 +408,31 @@ static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st, 
   E.launches++;
 }
 
+/* pseudo flux of tiles [tile0, tile0 + ntiles) from the device grad rows (flux.c:111-201) */
+static void flux_prepare(void)
+{
+  Engine &E = g_eng;
+  if (E.d_flux) return;
+  ASSERT(E.committed);
+  ASSERT((int)E.flux_smem <= 227 * 1024 - 64);
+  CUDA_CHECK(cudaMalloc(&E.d_flux, (size_t)E.rows * NFLUX * sizeof(double)));
+  CUDA_CHECK(cudaMemset(E.d_flux, 0, (size_t)E.rows * NFLUX * sizeof(double)));
+  CUDA_CHECK(cudaFuncSetAttribute(ggk::psd_flux_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E.flux_smem));
+  CUDA_CHECK(cudaFuncSetAttribute(ggk::psd_flux_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E.flux_smem));
+}
+static void launch_flux(long long tile0, long long ntiles, cudaStream_t st)
+{
+  Engine &E = g_eng;
+  if (ntiles <= 0) return;
+  flux_prepare();
+  if (E.exact)
+    ggk::psd_flux_tile_kernel<true><<<(unsigned)ntiles, E.block_threads, E.flux_smem, st>>>(E.d_tiles + tile0, E.d_blob, E.d_grad, E.d_flux);
+  else
+    ggk::psd_flux_tile_kernel<false><<<(unsigned)ntiles, E.block_threads, E.flux_smem, st>>>(E.d_tiles + tile0, E.d_blob, E.d_grad, E.d_flux);
+  CUDA_CHECK(cudaGetLastError());
+  E.launches++;
+}
+
 /* ------------------------------------------------------------------------------------------
  * commit: schedules, device layout, exchange plan
  * ---------------------------------------------------------------------------------------- */
@@ -449,6 +476,8 @@ extern "C" void cfdp_plan(void)
     E.nfaces += d->sch.nfaces_computed; E.nown += d->sch.nown; E.nall += d->sch.nall;
     E.tile_faces += d->sch.tile_faces; E.halo_refs += d->sch.halo_refs;
     E.alg_bytes += d->sch.nfaces_computed * 32 + (long long)d->sch.nall * 56 + (long long)d->sch.nown * 176;
+    /* pseudo flux: fpoint + fnormal per face, 72 of the 168 bytes of every grad row read once, 24 bytes of psd_flux written per own point */
+    E.flux_alg_bytes += d->sch.nfaces_computed * 32 + (long long)d->sch.nall * 72 + (long long)d->sch.nown * 24;
   }
   ASSERT(E.rows < 0x7FFFFFF0LL);
   E.h_tiles.resize((size_t)E.ntiles);
@@ -472,6 +501,7 @@ extern "C" void cfdp_plan(void)
       uint32_t *hr = (uint32_t *)(&s.blob[s.tile_blob[k]] + t.halo_off);
       for (int j = 0; j < s.tile_nhpos[k]; j++) if (hr[j] != 0xFFFFFFFFu) hr[j] += (uint32_t)d->rowbase;
       E.max_footprint = std::max(E.max_footprint, ggk::tile_footprint(t.blob_bytes, t.npts, t.nhalo));
+      E.flux_smem = std::max(E.flux_smem, ggk::flux_footprint(t.blob_bytes, t.npts, t.nhalo));
       E.h_tiles[(size_t)(k < s.nboundary ? tb++ : ti++)] = t;
     }
     E.point_of_row[i].assign((size_t)s.nrows, -1);
@@ -671,6 +701,34 @@ extern "C" void cfdp_grad_to_host(solver_data *sd)
   const size_t n = (size_t)sd->nallpoints;
   launch_rows_copy(E.d_stage, nullptr, E.d_grad, (const uint32_t *)E.d_rowmap[i], (long long)n, CFDP_DIM2, E.s_comp);
   CUDA_CHECK(cudaMemcpyAsync(&sd->grad[0][0][0], E.d_stage, n * CFDP_DIM2 * sizeof(double), cudaMemcpyDeviceToHost, E.s_comp));
+  CUDA_CHECK(cudaStreamSynchronize(E.s_comp));
+}
+
+/* sd->grad (all rows, ghosts included) -> device: what compute_psd_flux reads when the caller keeps its state on the host */
+extern "C" void cfdp_grad_to_device(solver_data *sd)
+{
+  Engine &E = g_eng;
+  cfdp_commit();
+  Domain *d = engine_find_domain(sd);
+  ASSERT(d != NULL);
+  const int i = hosted_index(d);
+  const size_t n = (size_t)sd->nallpoints;
+  CUDA_CHECK(cudaMemcpyAsync(E.d_stage, &sd->grad[0][0][0], n * CFDP_DIM2 * sizeof(double), cudaMemcpyHostToDevice, E.s_comp));
+  launch_rows_copy(E.d_grad, (const uint32_t *)E.d_rowmap[i], E.d_stage, nullptr, (long long)n, CFDP_DIM2, E.s_comp);
+}
+
+/* device pseudo flux -> own rows of sd->psd_flux (ghost rows are not defined, flux_kernels.cuh) */
+extern "C" void cfdp_flux_to_host(solver_data *sd)
+{
+  Engine &E = g_eng;
+  ASSERT(E.committed);
+  flux_prepare();
+  Domain *d = engine_find_domain(sd);
+  ASSERT(d != NULL);
+  const int i = hosted_index(d);
+  const size_t n = (size_t)sd->nownpoints;
+  launch_rows_copy(E.d_stage, nullptr, E.d_flux, (const uint32_t *)E.d_rowmap[i], (long long)n, NFLUX, E.s_comp);
+  CUDA_CHECK(cudaMemcpyAsync(&sd->psd_flux[0][0], E.d_stage, n * NFLUX * sizeof(double), cudaMemcpyDeviceToHost, E.s_comp));
   CUDA_CHECK(cudaStreamSynchronize(E.s_comp));
 }
 
@@ -891,12 +949,32 @@ extern "C" double cfdp_iterate(int variant, int niter, int final_last)
   ASSERT(variant >= CFDP_COMM_FREE && variant <= CFDP_GASPI_ASYNC);
   if (env_int("CFDP_TIMELINE", 0) && variant != CFDP_COMM_FREE) timeline_probe(variant);
   CUDA_CHECK(cudaEventRecord(E.ev_t0, E.s_comp));
-  for (int i = 0; i < niter; i++) run_iteration(variant);
+  for (int i = 0; i < niter; i++) {
+    run_iteration(variant);
+    if (E.with_flux) launch_flux(0, E.ntiles, E.s_comp); /* solver.c:45-55: gradient (+ exchange), then the pseudo flux; s_comp has joined the exchange */
+  }
   CUDA_CHECK(cudaEventRecord(E.ev_t1, E.s_comp));
   CUDA_CHECK(cudaEventSynchronize(E.ev_t1));
   float ms = 0;
   CUDA_CHECK(cudaEventElapsedTime(&ms, E.ev_t0, E.ev_t1));
   if (variant == CFDP_COMM_FREE && niter > 0) E.last_kernel_ms = ms / niter;
+  return (double)ms;
+}
+
+extern "C" void cfdp_set_flux(int on) { g_eng.with_flux = on ? 1 : 0; }
+
+/* niter pseudo-flux passes over all hosted domains on the device grad as it stands; returns the device time in ms */
+extern "C" double cfdp_flux_iterate(int niter)
+{
+  Engine &E = g_eng;
+  cfdp_commit();
+  CUDA_CHECK(cudaEventRecord(E.ev_t0, E.s_comp));
+  for (int i = 0; i < niter; i++) launch_flux(0, E.ntiles, E.s_comp);
+  CUDA_CHECK(cudaEventRecord(E.ev_t1, E.s_comp));
+  CUDA_CHECK(cudaEventSynchronize(E.ev_t1));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, E.ev_t0, E.ev_t1));
+  if (niter > 0) E.last_flux_ms = ms / niter;
   return (double)ms;
 }
 
@@ -1073,6 +1151,23 @@ extern "C" void compute_gradients_gg_mpifence_async(comm_data *cd, solver_data *
 extern "C" void compute_gradients_gg_mpipscw_bulk_sync(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_GASPI_BULK_SYNC, final); }
 extern "C" void compute_gradients_gg_mpipscw_async(comm_data *cd, solver_data *sd, int final) { gradients_entry(cd, sd, CFDP_GASPI_ASYNC, final); }
 
+/* flux.h:12.  Called by every OpenMP thread like the gradient (solver.c:52): only thread 0 acts; with several hosted
+ * domains the call for the first one drives all.  Reads sd->grad (host) unless cfdp_set_resident(1), writes the own
+ * rows of sd->psd_flux. */
+extern "C" void compute_psd_flux(solver_data *sd)
+{
+  ASSERT(sd != NULL);
+  if (omp_get_thread_num() != 0) return;
+  Engine &E = g_eng;
+  Domain *d = engine_find_domain(sd);
+  ASSERT(d != NULL);
+  cfdp_commit();
+  if (d != E.doms[0]) return;
+  if (!E.resident) for (Domain *h : E.doms) cfdp_grad_to_device(h->sd);
+  launch_flux(0, E.ntiles, E.s_comp);
+  if (!E.resident) for (Domain *h : E.doms) cfdp_flux_to_host(h->sd);
+}
+
 /* exchange_data_mpi.c:134-166 pre-posts MPI_Irecv; NCCL receives are enqueued together with the
  * sends, so this only validates its arguments */
 extern "C" void exchange_dbl_mpi_post_recv(comm_data *cd, int dim2)
@@ -1097,6 +1192,7 @@ extern "C" void cfdp_get_stats(cfdp_stats *st)
   st->alg_bytes = E.alg_bytes; st->h2d_bytes = E.nall * NGRAD * 8; st->d2h_bytes = E.nall * CFDP_DIM2 * 8;
   for (Domain *d : E.doms) { st->lds_wavefronts_min += d->sch.lds_wavefronts_min; st->lds_wavefronts_est += d->sch.lds_wavefronts_est; }
   st->launches = E.launches; st->last_kernel_ms = E.last_kernel_ms; st->smem_bytes = E.smem_bytes;
+  st->flux_alg_bytes = E.flux_alg_bytes; st->last_flux_ms = E.last_flux_ms; st->flux_smem_bytes = (int)E.flux_smem;
 }
 
 extern "C" int cfdp_get_schedule(const solver_data *sd, cfdp_schedule_view *v)
@@ -1217,7 +1313,7 @@ extern "C" void cfdp_finalize(void)
   if (E.have_device) {
     cudaDeviceSynchronize();
     if (E.comm) { g_nccl.CommDestroy(E.comm); E.comm = nullptr; }
-    cudaFree(E.d_var); cudaFree(E.d_grad); cudaFree(E.d_pvol); cudaFree(E.d_blob); cudaFree(E.d_tiles); cudaFree(E.d_stage);
+    cudaFree(E.d_var); cudaFree(E.d_grad); cudaFree(E.d_pvol); cudaFree(E.d_flux); E.d_flux = nullptr; cudaFree(E.d_blob); cudaFree(E.d_tiles); cudaFree(E.d_stage);
     cudaFree(E.d_loc_dst); cudaFree(E.d_loc_src); cudaFree(E.d_exp_off); cudaFree(E.d_exp_src); cudaFree(E.d_exp_dst); cudaFree(E.d_send_rows); cudaFree(E.d_recv_rows); cudaFree(E.d_sendbuf); cudaFree(E.d_recvbuf);
     for (int *p : E.d_rowmap) cudaFree(p);
   }
@@ -1253,7 +1349,7 @@ extern "C" void cfdp_finalize(void)
   E.committed = false; E.planned = false; E.configured = false;
   E.h_exp_off.clear(); E.h_exp_src.clear(); E.h_exp_dst.clear(); E.d_exp_off = E.d_exp_src = E.d_exp_dst = nullptr;
   E.h_tiles.clear(); E.blob_base.clear(); E.h_loc_dst.clear(); E.h_loc_src.clear(); E.h_send_rows.clear(); E.h_recv_rows.clear();
-  E.max_nfaces = E.max_nloc = E.max_npts = 0; E.max_stage = 0; E.blob_bytes = 0; E.max_blob = 0; E.max_nhalo = 0; E.max_footprint = 0;
+  E.max_nfaces = E.max_nloc = E.max_npts = 0; E.max_stage = 0; E.blob_bytes = 0; E.max_blob = 0; E.max_nhalo = 0; E.max_footprint = 0; E.flux_smem = 0; E.with_flux = 0; E.flux_alg_bytes = 0;
   E.rows = E.ntiles = E.nbtiles = 0; E.nfaces = E.nown = E.nall = E.tile_faces = E.halo_refs = E.alg_bytes = 0;
   E.n_local = E.n_send = E.n_recv = 0; E.launches = 0; E.nprocs = 0; E.per_proc = 0;
 }

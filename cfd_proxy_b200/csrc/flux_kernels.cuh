@@ -1,0 +1,140 @@
+/*
+ * flux_kernels.cuh -- the pseudo flux (src/flux.c:111-201), the step that consumes the exchanged gradients
+ * (SURVEY 8f row f3), on the tile schedule of the gradient kernel (schedule.cpp).
+ *
+ * What flux.c computes, per face (p0, p1) with area vector n:
+ *   d[eq][c]   = 0.5 * (grad[p0][eq][c] + grad[p1][eq][c])        eq = IVX..IVZ (0..2), c = x,y,z   (flux.c:153-163)
+ *   sts_xx     = lambda * (d[1][1] + d[2][2] - 2*d[0][0]), ...     lambda = -2/3 * mue_eff, mue_eff = 1 (:165-173)
+ *   flux_IVX   = -(sts_xx*nx + sts_xy*ny + sts_xz*nz), ...         (:175-177)
+ *   if (ftype != 3) psd_flux[p0] += flux;  if (ftype != 2) psd_flux[p1] -= flux;               (:179-190)
+ * where ftype is the face type of the colour: 1 = p0 not written by this thread, 2 = p1 not written, 3 = both
+ * written (rangelist.c:719-736).  The tests differ from gradients.c (:64, :86, :108): a face between two own points
+ * only updates p1, a face whose p1 is a ghost updates p0.  The GPU kernel restates exactly that for a single-thread
+ * run (ftype 1 <=> p0 is a ghost, 2 <=> p1 is a ghost): an own point p receives
+ *   - flux   from every face where it is p1,
+ *   + flux   from the faces where it is p0 and p1 is a ghost,
+ * summed from 0 in the reference's face order.  Ghost rows of psd_flux are not defined by the reference (they are
+ * accumulated into without ever being zeroed) and are not written.
+ *
+ * One CTA per tile, two or more CTAs per SM.  The tile blob (normals, halo row list, ELL adjacency) arrives by one
+ * TMA bulk copy; the first 72 bytes (grad[p][0..2][0..2]) of the grad rows of the tile's own and halo points are
+ * gathered with 8-byte cp.async.  One thread per own point walks its ELL column; nothing is written to shared
+ * memory after the loads.  ELL entry: local point | ghost << 15 | face slot << 16 | (point is p1) << 31.
+ * EXACT = IEEE multiply and add in the reference's expression order (bit-identical to the reference built without
+ * FMA); otherwise the compiler may contract.
+ */
+#ifndef CFDP_FLUX_KERNELS_CUH
+#define CFDP_FLUX_KERNELS_CUH
+
+#include "gg_kernels.cuh"
+
+namespace ggk {
+
+#define CFDP_FLUX_ROW 9 /* doubles of a grad row the flux reads: [IVX..IVZ][0..2] (flux.h:7-9) */
+
+__host__ __device__ __forceinline__ uint32_t flux_rows_off(uint32_t blob_bytes) { return (blob_bytes + 127u) & ~127u; }
+__host__ __device__ __forceinline__ uint32_t flux_footprint(uint32_t blob_bytes, uint32_t npts, uint32_t nhalo)
+{
+  return flux_rows_off(blob_bytes) + (CFDP_HALO_BASE(npts) + nhalo) * (CFDP_FLUX_ROW * 8);
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void face_flux(const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ n,
+                                          double &fx, double &fy, double &fz)
+{
+  const double lambda = -2.0 / 3.0; /* -2/3 * mue_eff, mue_eff = 1 (flux.c:123, :165) */
+  if (EXACT) {
+    double d[CFDP_FLUX_ROW];
+#pragma unroll
+    for (int k = 0; k < CFDP_FLUX_ROW; k++) d[k] = __dmul_rn(0.5, __dadd_rn(a[k], b[k]));
+    /* d[0..2] = dvx_dx,dy,dz   d[3..5] = dvy_dx,dy,dz   d[6..8] = dvz_dx,dy,dz */
+    const double sxx = __dmul_rn(lambda, __dadd_rn(__dadd_rn(d[4], d[8]), -__dmul_rn(2.0, d[0])));
+    const double syy = __dmul_rn(lambda, __dadd_rn(__dadd_rn(d[0], d[8]), -__dmul_rn(2.0, d[4])));
+    const double szz = __dmul_rn(lambda, __dadd_rn(__dadd_rn(d[0], d[4]), -__dmul_rn(2.0, d[8])));
+    const double sxy = __dadd_rn(d[1], d[3]), sxz = __dadd_rn(d[2], d[6]), syz = __dadd_rn(d[5], d[7]);
+    fx = -__dadd_rn(__dadd_rn(__dmul_rn(sxx, n[0]), __dmul_rn(sxy, n[1])), __dmul_rn(sxz, n[2]));
+    fy = -__dadd_rn(__dadd_rn(__dmul_rn(sxy, n[0]), __dmul_rn(syy, n[1])), __dmul_rn(syz, n[2]));
+    fz = -__dadd_rn(__dadd_rn(__dmul_rn(sxz, n[0]), __dmul_rn(syz, n[1])), __dmul_rn(szz, n[2]));
+  } else {
+    double d[CFDP_FLUX_ROW];
+#pragma unroll
+    for (int k = 0; k < CFDP_FLUX_ROW; k++) d[k] = 0.5 * (a[k] + b[k]);
+    const double sxx = lambda * (d[4] + d[8] - 2.0 * d[0]);
+    const double syy = lambda * (d[0] + d[8] - 2.0 * d[4]);
+    const double szz = lambda * (d[0] + d[4] - 2.0 * d[8]);
+    const double sxy = d[1] + d[3], sxz = d[2] + d[6], syz = d[5] + d[7];
+    fx = -(sxx * n[0] + sxy * n[1] + sxz * n[2]);
+    fy = -(sxy * n[0] + syy * n[1] + syz * n[2]);
+    fz = -(sxz * n[0] + syz * n[1] + szz * n[2]);
+  }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(CFDP_MAX_TILE_POINTS, 2)
+psd_flux_tile_kernel(const TileDesc *__restrict__ tiles, const unsigned char *__restrict__ blob,
+                     const double *__restrict__ grad, double *__restrict__ flux)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full;
+  const TileDesc td = tiles[blockIdx.x];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int npts = td.npts, nhalo = td.nhalo, n_even = CFDP_HALO_BASE(npts);
+  const unsigned char *tb = blob + td.blob;
+  double *s_rows = reinterpret_cast<double *>(smem + flux_rows_off(td.blob_bytes));
+
+  if (tid == 0) {
+    mbar_init(&full, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(&full, td.blob_bytes);
+    bulk_g2s_hint(smem, tb, td.blob_bytes, &full, l2_policy_evict_first());
+  }
+  { /* own rows: consecutive lanes = consecutive words of a row (72 of its 168 bytes) */
+    const double *g = grad + (size_t)td.row0 * (NGRAD * 3);
+    const int nw = npts * CFDP_FLUX_ROW;
+    for (int i = tid; i < nw; i += nthr) {
+      const int r = i / CFDP_FLUX_ROW, c = i - r * CFDP_FLUX_ROW;
+      cp_async8(s_rows + i, g + (size_t)r * (NGRAD * 3) + c);
+    }
+  }
+  { /* halo rows, through the tile's halo row list (read from global memory: the blob is still in flight) */
+    const uint32_t *hrows = reinterpret_cast<const uint32_t *>(tb + td.halo_off);
+    double *s = s_rows + n_even * CFDP_FLUX_ROW;
+    const int nw = nhalo * CFDP_FLUX_ROW;
+    for (int i = tid; i < nw; i += nthr) {
+      const int r = i / CFDP_FLUX_ROW, c = i - r * CFDP_FLUX_ROW;
+      const uint32_t row = __ldg(hrows + r);
+      if (row != 0xFFFFFFFFu) cp_async8(s + i, grad + (size_t)row * (NGRAD * 3) + c);
+    }
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();          /* everybody's rows have landed; the mbarrier initialisation is visible */
+  mbar_wait(&full, 0);      /* the blob has landed */
+
+  if (tid < npts) {
+    const double *s_nrm = reinterpret_cast<const double *>(smem);
+    const uint32_t *ell = reinterpret_cast<const uint32_t *>(smem + td.halo_off + ((nhalo * 4 + 15) & ~15)) + tid;
+    const int npad = td.npad, maxdeg = td.maxdeg;
+    double a[CFDP_FLUX_ROW];
+#pragma unroll
+    for (int k = 0; k < CFDP_FLUX_ROW; k++) a[k] = s_rows[tid * CFDP_FLUX_ROW + k];
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    uint32_t e_next = maxdeg > 0 ? ell[0] : CFDP_ADJ_PAD;
+    for (int j = 0; j < maxdeg; j++) {
+      const uint32_t e = e_next;
+      e_next = j + 1 < maxdeg ? ell[(j + 1) * npad] : CFDP_ADJ_PAD;
+      if (e == CFDP_ADJ_PAD) continue;
+      const bool is_p1 = (e & 0x80000000u) != 0;
+      if (!is_p1 && !(e & 0x8000u)) continue; /* this point is p0 and p1 is an own point: flux.c:179 skips p0 (ftype 3) */
+      double fx, fy, fz;
+      face_flux<EXACT>(a, s_rows + CFDP_FLUX_ROW * (e & 0x7FFFu), s_nrm + 3 * ((e >> 16) & 0x7FFFu), fx, fy, fz);
+      if (is_p1) { fx = -fx; fy = -fy; fz = -fz; }   /* psd_flux[p1] -= flux (flux.c:185-190) */
+      ax = __dadd_rn(ax, fx); ay = __dadd_rn(ay, fy); az = __dadd_rn(az, fz);
+    }
+    double *o = flux + (size_t)(td.row0 + tid) * NFLUX;
+    o[0] = ax; o[1] = ay; o[2] = az;
+  }
+}
+
+} // namespace ggk
+#endif

@@ -118,7 +118,7 @@ __device__ __forceinline__ void walk_faces(const uint32_t *__restrict__ ell, int
     e_next = j + 1 < maxdeg ? ell[(j + 1) * npad] : CFDP_ADJ_PAD;
     if (e == CFDP_ADJ_PAD) continue;
     const double *n = s_nrm + 3 * ((e >> 16) & 0x7FFFu);
-    const double *w = s_hvar + NGRAD * (e & 0xFFFFu) + LO;
+    const double *w = s_hvar + NGRAD * (e & 0x7FFFu) + LO; /* bit 15: the neighbour is a ghost (flux_kernels.cuh) */
     const uint32_t sb = e & 0x80000000u;      /* this point is p1 of the face: grad[p1] -= n*val (gradients.c:101-105) */
     const double nx = flip_sign(n[0], sb), ny = flip_sign(n[1], sb), nz = flip_sign(n[2], sb);
 #pragma unroll

@@ -17,7 +17,8 @@
  * A tile = up to `tile_points` own points.  Its blob holds the normals of every face
  * incident to a tile point (read once per tile), the device rows of the non-tile end points
  * (halo of the tile) and a point-centric ELL adjacency: entry = neighbour's tile-local
- * index | face slot << 16 | sign << 31.  A point's entries are sorted by the reference's
+ * index | ghost << 15 | face slot << 16 | sign << 31 (ghost: the neighbour is an addpoint of the domain; only the
+ * pseudo-flux kernel looks at it).  A point's entries are sorted by the reference's
  * single-thread face order (ttype, p1, p0) (rangelist.c:567-608, util.c:113-136), so the
  * device sum runs over the same addends in the same order as the reference with one thread.
  *
@@ -571,7 +572,9 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
         for (int j = 0; j < deg[i]; j++) {
           const Ent &e = tile_ents[(size_t)i * md + j];
           const uint32_t loc = e.nbr < n ? (uint32_t)e.nbr : (uint32_t)(n_even + hpos_of[e.nbr - n]);
-          ell[(size_t)j * npad + i] = loc | ((uint32_t)slot_of[e.fid] << 16) | (e.sign << 31);
+          const uint32_t ghost = (e.nbr >= n && hpts[e.nbr - n] >= sd->nownpoints) ? 0x8000u : 0u;
+          ASSERT(loc < 0x8000u);
+          ell[(size_t)j * npad + i] = loc | ghost | ((uint32_t)slot_of[e.fid] << 16) | (e.sign << 31);
         }
 
       /* shared-memory wavefront estimate of the face walk: 7 var words + 3 normal words per face end */
@@ -585,7 +588,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
             const uint32_t e = ell[(size_t)j * npad + i];
             if (e == CFDP_ADJ_PAD) continue;
             nact++;
-            const uint32_t r = e & 0xFFFFu, sl = (e >> 16) & 0x7FFFu;
+            const uint32_t r = e & 0x7FFFu, sl = (e >> 16) & 0x7FFFu;
             bool dup = false;
             for (int t = 0; t < nsv; t++) if (seen_v[t] == r) dup = true;
             if (!dup) { seen_v[nsv++] = r; cnt_v[r & 15]++; }

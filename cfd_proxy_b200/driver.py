@@ -35,6 +35,10 @@ class HostedDomain:
         return np.ctypeslib.as_array(self.sd.grad, shape=(self.sd.nallpoints, 7, 3))
 
     @property
+    def psd_flux(self) -> np.ndarray:
+        return np.ctypeslib.as_array(self.sd.psd_flux, shape=(self.sd.nallpoints, 3))
+
+    @property
     def fpoint(self) -> np.ndarray:
         return np.ctypeslib.as_array(self.sd.fpoint, shape=(self.sd.nfaces, 2))
 
@@ -180,6 +184,27 @@ class Session:
     def download_grad(self):
         for d in self.domains:
             self.lib.cfdp_grad_to_host(C.byref(d.sd))
+
+    def upload_grad(self):
+        for d in self.domains:
+            self.lib.cfdp_grad_to_device(C.byref(d.sd))
+        self.lib.cfdp_device_synchronize()
+
+    def download_flux(self):
+        for d in self.domains:
+            self.lib.cfdp_flux_to_host(C.byref(d.sd))
+
+    def set_flux(self, on=True):
+        """cfdp_iterate also runs the pseudo flux after every gradient + exchange (solver.c:45-55)."""
+        self.lib.cfdp_set_flux(1 if on else 0)
+
+    def flux_iterate(self, niter=1) -> float:
+        """Pseudo-flux passes only, on the device grad as it stands; returns device milliseconds."""
+        return self.lib.cfdp_flux_iterate(niter)
+
+    def psd_flux(self):
+        """The reference-named entry point (flux.h:12) for all hosted domains: host grad in, host psd_flux out."""
+        self.lib.compute_psd_flux(C.byref(self.domains[0].sd))
 
     def iterate(self, variant="mpi_async", niter=1) -> float:
         """Device-resident iterations over all hosted domains; returns device milliseconds."""

@@ -88,7 +88,8 @@ class Stats(C.Structure):
         "lds_wavefronts_min", "lds_wavefronts_est")] + [
         ("last_kernel_ms", C.c_double),
         ("nprocs", C.c_int), ("proc_rank", C.c_int), ("ndomains_hosted", C.c_int),
-        ("tile_points", C.c_int), ("smem_bytes", C.c_int),
+        ("tile_points", C.c_int), ("smem_bytes", C.c_int), ("flux_smem_bytes", C.c_int),
+        ("flux_alg_bytes", C.c_longlong), ("last_flux_ms", C.c_double),
     ]
 
 
@@ -116,7 +117,8 @@ EXPORTED = [
     "compute_gradients_gg_gaspi_bulk_sync", "compute_gradients_gg_gaspi_async",
     "compute_gradients_gg_mpifence_bulk_sync", "compute_gradients_gg_mpifence_async",
     "compute_gradients_gg_mpipscw_bulk_sync", "compute_gradients_gg_mpipscw_async",
-    "exchange_dbl_mpi_post_recv", "get_nc_val", "get_nc_int", "get_nc_double",
+    "exchange_dbl_mpi_post_recv", "compute_psd_flux", "cfdp_grad_to_device", "cfdp_flux_to_host", "cfdp_set_flux", "cfdp_flux_iterate",
+    "get_nc_val", "get_nc_int", "get_nc_double",
     "cfdp_nc_open", "cfdp_nc_close", "cfdp_nc_strerror", "cfdp_nc_inq_dimid", "cfdp_nc_inq_dimlen",
     "cfdp_nc_inq_varid", "cfdp_nc_get_var_int", "cfdp_nc_get_var_double",
     "cfdp_configure", "cfdp_init_communication_domain", "cfdp_nccl_get_unique_id", "cfdp_nccl_init",
@@ -158,6 +160,11 @@ def load() -> C.CDLL:
               "mpifence_bulk_sync", "mpifence_async", "mpipscw_bulk_sync", "mpipscw_async"):
         sig("compute_gradients_gg_" + v, None, cd_p, sd_p, C.c_int)
     sig("exchange_dbl_mpi_post_recv", None, cd_p, C.c_int)
+    sig("compute_psd_flux", None, sd_p)
+    sig("cfdp_grad_to_device", None, sd_p)
+    sig("cfdp_flux_to_host", None, sd_p)
+    sig("cfdp_set_flux", None, C.c_int)
+    sig("cfdp_flux_iterate", C.c_double, C.c_int)
     sig("get_nc_val", C.c_int, C.c_int, C.c_char_p)
     sig("get_nc_int", None, C.c_int, C.c_char_p, c_int_p)
     sig("get_nc_double", None, C.c_int, C.c_char_p, c_dbl_p)

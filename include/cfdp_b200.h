@@ -126,6 +126,11 @@ void compute_gradients_gg_mpifence_async(comm_data *cd, solver_data *sd, int fin
 void compute_gradients_gg_mpipscw_bulk_sync(comm_data *cd, solver_data *sd, int final);
 void compute_gradients_gg_mpipscw_async(comm_data *cd, solver_data *sd, int final);
 void exchange_dbl_mpi_post_recv(comm_data *cd, int dim2);
+/* flux.h:12 (flux.c:193-201), the consumer of the exchanged gradients, called once per iteration after
+ * compute_gradients_gg_* (solver.c:52).  Reads sd->grad[p][IVX..IVZ][0..2] of both end points of every face,
+ * writes the own rows of sd->psd_flux.  Results are those of the reference run with one OpenMP thread (with more
+ * threads the reference's `ftype` tests make the result depend on the thread partition, flux.c:179-190). */
+void compute_psd_flux(solver_data *sd);
 
 int  get_nc_val(int ncid, const char *name);
 void get_nc_int(int ncid, const char *name, int *array);
@@ -185,6 +190,8 @@ void cfdp_plan(void);
 /* host<->device mirrors (SURVEY 8(b) ownership): var is uploaded, grad downloaded */
 void cfdp_var_to_device(solver_data *sd);
 void cfdp_grad_to_host(solver_data *sd);
+void cfdp_grad_to_device(solver_data *sd);   /* all rows of sd->grad, ghosts included */
+void cfdp_flux_to_host(solver_data *sd);     /* own rows of sd->psd_flux */
 /* resident = 1: compute_gradients_gg_* leave var/grad on the device (no per-call PCIe copies);
  * resident = 0 (default): every call uploads sd->var and downloads sd->grad (true drop-in) */
 void cfdp_set_resident(int resident);
@@ -194,6 +201,10 @@ void cfdp_set_exact(int exact);
 /* run `niter` iterations of variant over ALL hosted domains, device resident; returns the
  * device time in milliseconds (CUDA events on the compute stream) */
 double cfdp_iterate(int variant, int niter, int final_last);
+/* on = 1: every iteration of cfdp_iterate also runs the pseudo flux after the exchange (solver.c:45-55) */
+void cfdp_set_flux(int on);
+/* `niter` pseudo-flux passes over all hosted domains on the device grad as it stands; device time in ms */
+double cfdp_flux_iterate(int niter);
 /* one end-to-end step over all hosted domains: H2D var, iterate once, D2H grad (host buffers) */
 double cfdp_step_e2e(int variant);
 void cfdp_device_synchronize(void);
@@ -214,6 +225,9 @@ typedef struct {
   long long lds_wavefronts_min, lds_wavefronts_est; /* schedule quality: shared-memory wavefronts of the face walk, conflict-free vs estimated */
   double last_kernel_ms;     /* mean device time of the gradient kernel(s) per iteration in the last cfdp_iterate */
   int nprocs, proc_rank, ndomains_hosted, tile_points, smem_bytes;
+  int flux_smem_bytes;       /* shared memory per CTA of the pseudo-flux kernel */
+  long long flux_alg_bytes;  /* algorithmic bytes of one pseudo-flux pass: 32 B per face + 72 B per point + 24 B per own point */
+  double last_flux_ms;       /* mean device time of one pseudo-flux pass in the last cfdp_flux_iterate */
 } cfdp_stats;
 void cfdp_get_stats(cfdp_stats *st);
 

@@ -33,6 +33,8 @@ def lib():
         ip, dp, up = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_ubyte)
         _lib.oracle_gradients.restype = C.c_long
         _lib.oracle_gradients.argtypes = [C.c_int, C.c_int, C.c_int, ip, dp, dp, dp, dp, up, C.c_int]
+        _lib.oracle_psd_flux.restype = C.c_long
+        _lib.oracle_psd_flux.argtypes = [C.c_int, C.c_int, C.c_int, ip, dp, dp, dp, up, C.c_int]
         _lib.oracle_error_scale.restype = None
         _lib.oracle_error_scale.argtypes = [C.c_int, C.c_int, ip, dp, dp, dp, dp]
         _lib.oracle_pack.argtypes = [dp, C.c_int, ip, C.c_int, dp]
@@ -60,6 +62,45 @@ def gradients(dom, var, grad_in=None, is_send=None, order=1):
                            _p(var, C.c_double), _p(grad, C.c_double),
                            _p(send, C.c_ubyte) if send is not None else None, order)
     return grad
+
+
+def psd_flux(dom, grad, flux_in=None, is_send=None, order=1):
+    """Pseudo flux of one domain from its (exchanged) grad[nall,7,3] (flux.c:111-201, single-thread semantics).
+    Returns psd_flux[nall,3]; only own rows are defined, the others keep flux_in (NaN by default)."""
+    nall, nown = int(dom["nall"]), int(dom["nown"])
+    fp = np.ascontiguousarray(dom["fpoint"], dtype=np.int32)
+    fn = np.ascontiguousarray(dom["fnormal"], dtype=np.float64)
+    grad = np.ascontiguousarray(grad, dtype=np.float64).reshape(nall, 21)
+    out = np.full((nall, 3), np.nan) if flux_in is None else np.array(flux_in, dtype=np.float64).reshape(nall, 3).copy()
+    send = np.ascontiguousarray(is_send, dtype=np.uint8) if is_send is not None else None
+    lib().oracle_psd_flux(len(fp), nown, nall, _p(fp, C.c_int), _p(fn, C.c_double), _p(grad, C.c_double), _p(out, C.c_double),
+                          _p(send, C.c_ubyte) if send is not None else None, order)
+    return out
+
+
+def psd_flux_numpy(dom, grad):
+    """Independent vectorised restatement of flux.c:111-201 for a single-thread run (np.add.at, file order):
+    returns (psd_flux[nown,3], error scale S_p[nown]) -- cross-check of oracle_psd_flux and the tolerance of the
+    fused-multiply-add mode: |a-b| <= 1e-12*|b| + 64*eps*S_p, S_p = sum over contributing faces of 4*|n_f|_1*max|d_f|."""
+    nown = int(dom["nown"])
+    fp, fn = dom["fpoint"], dom["fnormal"]
+    keep = (fp[:, 0] < nown) | (fp[:, 1] < nown)
+    fp, fn = fp[keep], fn[keep]
+    g = np.asarray(grad, dtype=np.float64).reshape(-1, 21)[:, :9]
+    d = 0.5 * (g[fp[:, 0]] + g[fp[:, 1]])                        # [F,9]: dvx_dx,dy,dz, dvy_..., dvz_...
+    lam = -2.0 / 3.0
+    sxx = lam * (d[:, 4] + d[:, 8] - 2.0 * d[:, 0]); syy = lam * (d[:, 0] + d[:, 8] - 2.0 * d[:, 4]); szz = lam * (d[:, 0] + d[:, 4] - 2.0 * d[:, 8])
+    sxy = d[:, 1] + d[:, 3]; sxz = d[:, 2] + d[:, 6]; syz = d[:, 5] + d[:, 7]
+    nx, ny, nz = fn[:, 0], fn[:, 1], fn[:, 2]
+    fl = -np.stack([sxx * nx + sxy * ny + sxz * nz, sxy * nx + syy * ny + syz * nz, sxz * nx + syz * ny + szz * nz], axis=1)
+    ftype = np.where(fp[:, 0] >= nown, 1, np.where(fp[:, 1] >= nown, 2, 3))
+    out = np.zeros((nown, 3)); scale = np.zeros(nown)
+    mag = 4.0 * np.abs(fn).sum(axis=1) * np.abs(d).max(axis=1)
+    w0 = (ftype != 3) & (fp[:, 0] < nown)
+    w1 = (ftype != 2) & (fp[:, 1] < nown)
+    np.add.at(out, fp[w0, 0], fl[w0]); np.add.at(scale, fp[w0, 0], mag[w0])
+    np.subtract.at(out, fp[w1, 1], fl[w1]); np.add.at(scale, fp[w1, 1], mag[w1])
+    return out, scale
 
 
 def error_scale(dom, var):
@@ -137,9 +178,9 @@ def have_ref():
     return all(os.path.exists(os.path.join(REF_DIR, x)) for x in ("ref_harness", "mpirun_shim"))
 
 
-def run_ref(prefix, lvl, ndomains, variant, niter, outprefix, threads=1, repeats=1, timeout=600):
-    """Run the reference harness (one rank per domain) and return per-domain grad/index/time."""
-    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+def run_ref(prefix, lvl, ndomains, variant, niter, outprefix, threads=1, repeats=1, timeout=600, with_flux=False):
+    """Run the reference harness (one rank per domain) and return per-domain grad/index/time (and psd_flux)."""
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), REF_WITH_FLUX="1" if with_flux else "0")
     cmd = [os.path.join(REF_DIR, "mpirun_shim"), "-np", str(ndomains), os.path.join(REF_DIR, "ref_harness"),
            "-lvl", str(lvl), prefix, variant, str(niter), outprefix, str(repeats)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
@@ -158,4 +199,6 @@ def run_ref(prefix, lvl, ndomains, variant, niter, outprefix, threads=1, repeats
             ridx[k] = raw[pos:pos + rc].copy(); pos += rc
         t = json.loads(open(f"{outprefix}_domain_{d}.time").read())
         res.append(dict(grad=g, sendindex=sidx, recvindex=ridx, time=t))
+        if with_flux:
+            res[-1]["psd_flux"] = np.fromfile(f"{outprefix}_domain_{d}.flux", dtype="<f8").reshape(-1, 3)
     return res

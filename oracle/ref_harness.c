@@ -6,7 +6,8 @@
  * src/hybrid.f6.c:27-101 and src/solver.c:35-120 do, but
  *   - overwrites sd.var with seeded data from "<meshfile>.var" (the shipped var == 1.0 makes
  *     interior gradients cancel), and pre-fills grad with NaN,
- *   - runs ONE variant for NITER iterations of gradient(+exchange) only (no pseudo flux),
+ *   - runs ONE variant for NITER iterations of gradient(+exchange) only; with REF_WITH_FLUX=1 in the
+ *     environment every iteration also calls compute_psd_flux like solver.c:45-55 does, and psd_flux is dumped,
  *   - dumps grad, sendindex/recvindex and timing for the parity tests and the CPU baseline.
  *
  *   ref_harness -lvl L PREFIX VARIANT NITER OUTPREFIX [REPEATS]
@@ -24,6 +25,7 @@
 #include "solver_data.h"
 #include "rangelist.h"
 #include "gradients.h"
+#include "flux.h"
 #include "exchange_data_mpi.h"
 #include "error_handling.h"
 #include "util.h"
@@ -64,6 +66,8 @@ int main(int argc, char *argv[])
   char *env = getenv("OMP_NUM_THREADS");
   ASSERT(env != NULL);
   const int NTHREADS = atoi(env);
+  const char *wf = getenv("REF_WITH_FLUX");
+  const int with_flux = wf && atoi(wf);
 
   init_communication(argc, argv, &cd);
   char fname[512];
@@ -107,12 +111,16 @@ int main(int argc, char *argv[])
     double t = -now();
     MPI_Barrier(MPI_COMM_WORLD);
     if (post) exchange_dbl_mpi_post_recv(&cd, NGRAD * 3);
-#pragma omp parallel default(none) shared(cd, sd, fn)
+#pragma omp parallel default(none) shared(cd, sd, fn) firstprivate(with_flux)
     {
       for (int i = 0; i < sd.niter; ++i) {
         int final = (i == sd.niter - 1) ? 1 : 0;
         fn(&cd, &sd, final);
 #pragma omp barrier
+        if (with_flux) {
+          compute_psd_flux(&sd);
+#pragma omp barrier
+        }
       }
     }
     MPI_Barrier(MPI_COMM_WORLD);
@@ -127,14 +135,21 @@ int main(int argc, char *argv[])
   ASSERT(gf != NULL);
   fwrite(&sd.grad[0][0][0], sizeof(double), (size_t)sd.nallpoints * NGRAD * 3, gf);
   fclose(gf);
+  if (with_flux) {
+    snprintf(path, sizeof path, "%s_domain_%d.flux", outprefix, cd.iProc);
+    FILE *ff = fopen(path, "wb");
+    ASSERT(ff != NULL);
+    fwrite(&sd.psd_flux[0][0], sizeof(double), (size_t)sd.nallpoints * NFLUX, ff);
+    fclose(ff);
+  }
   snprintf(path, sizeof path, "%s_domain_%d.index", outprefix, cd.iProc);
   dump_index(path, &cd);
   snprintf(path, sizeof path, "%s_domain_%d.time", outprefix, cd.iProc);
   FILE *tf = fopen(path, "w");
   ASSERT(tf != NULL);
   fprintf(tf, "{\"variant\": \"%s\", \"rank\": %d, \"nranks\": %d, \"threads\": %d, \"niter\": %d, \"repeats\": %d, "
-              "\"faces\": %ld, \"best_s\": %.9g, \"mean_s\": %.9g}\n",
-          variant, cd.iProc, cd.nProc, NTHREADS, niter, repeats, nf, best, sum / repeats);
+              "\"with_flux\": %d, \"faces\": %ld, \"best_s\": %.9g, \"mean_s\": %.9g}\n",
+          variant, cd.iProc, cd.nProc, NTHREADS, niter, repeats, with_flux, nf, best, sum / repeats);
   fclose(tf);
 
   free_communication_ressources(&cd);

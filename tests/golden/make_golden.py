@@ -6,7 +6,9 @@ domain over the shared-memory MPI shim) on small F6-schema stand-in meshes.  Run
 
 Each fixture <name>.npz holds, per domain d: the mesh spec (regenerated deterministically by
 cfd_proxy_b200.mesh), grad_<variant>_t<threads>_d<d> (float64 bit patterns stored as uint64), sendindex /
-recvindex as flat arrays, so that tests can check
+recvindex as flat arrays, flux_<variant>_t1_d<d> = psd_flux after gradient + exchange + compute_psd_flux
+(src/flux.c; one thread, the only thread count for which the reference's result is a function of the mesh), so that
+tests can check
   * the oracle restatement (oracle/gg_oracle.c) against the real reference  (pins the oracle),
   * the CUDA path against the real reference's numbers on the GPU box.
 """
@@ -51,6 +53,10 @@ def main():
                             out[f"sendindex_d{d}_k{k}"] = idx
                         for k, idx in r["recvindex"].items():
                             out[f"recvindex_d{d}_k{k}"] = idx
+        res = O.run_ref(prefix, lvl, nd, variants[-1], 2, os.path.join(tmp, "o_flux"), threads=1, with_flux=True)
+        for d, r in enumerate(res):
+            assert np.array_equal(r["grad"].view(np.uint64), out[f"grad_{variants[-1]}_t1_d{d}"])
+            out[f"flux_{variants[-1]}_t1_d{d}"] = r["psd_flux"].view(np.uint64)
         np.savez_compressed(os.path.join(here, name + ".npz"), **out)
         print(name, "->", os.path.getsize(os.path.join(here, name + ".npz")), "bytes")
 

@@ -19,6 +19,10 @@ def golden_grad(z, variant, threads, d):
     return z[f"grad_{variant}_t{threads}_d{d}"].view(np.float64)
 
 
+def golden_flux(z, variant, d):
+    return z[f"flux_{variant}_t1_d{d}"].view(np.float64)
+
+
 def golden_index(z, d, nd):
     send = {k: z[f"sendindex_d{d}_k{k}"] for k in range(nd) if f"sendindex_d{d}_k{k}" in z}
     recv = {k: z[f"recvindex_d{d}_k{k}"] for k in range(nd) if f"recvindex_d{d}_k{k}" in z}

@@ -8,7 +8,7 @@ import pytest
 
 import cfd_proxy_b200.mesh as M
 from oracle import oracle as O
-from helpers import GOLDEN, bits_differ, golden_grad, golden_index, load_golden
+from helpers import GOLDEN, bits_differ, golden_flux, golden_grad, golden_index, load_golden
 
 EPS = np.finfo(np.float64).eps
 
@@ -51,6 +51,22 @@ def test_oracle_within_tolerance_of_threaded_reference(name):
         scale = O.error_scale(d, var)[:, None, None]
         err = np.abs(ref[:d["nown"]] - g[:d["nown"]])
         assert (err <= 1e-12 * np.abs(g[:d["nown"]]) + 64 * EPS * scale).all()
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_flux_oracle_bit_identical_to_reference_one_thread(name):
+    """oracle_psd_flux (flux.c:111-201 restated) on the reference's own exchanged gradients == the reference's psd_flux."""
+    z, spec, doms, lvl = load_golden(name)
+    nd = len(doms)
+    recv, send = O.recvsend_index(doms) if nd > 1 else ([{}], [{}])
+    v = "mpi_async" if nd > 1 else "comm_free"
+    for a, d in enumerate(doms):
+        nown = d["nown"]
+        fl = O.psd_flux(d, golden_grad(z, v, 1, a), is_send=O.is_send_mask(d, send[a]), order=1)
+        assert bits_differ(golden_flux(z, v, a)[:nown], fl[:nown]) == 0
+        assert np.isnan(fl[nown:]).all()                   # ghost rows are not defined and not written
+        fl2, scale = O.psd_flux_numpy(d, golden_grad(z, v, 1, a))
+        assert (np.abs(fl2 - fl[:nown]) <= 64 * EPS * scale[:, None]).all()   # independent restatement, other summation order
 
 
 def test_numpy_restatement_agrees():

@@ -501,7 +501,7 @@ extern "C" void cfdp_plan(void)
       uint32_t *hr = (uint32_t *)(&s.blob[s.tile_blob[k]] + t.halo_off);
       for (int j = 0; j < s.tile_nhpos[k]; j++) if (hr[j] != 0xFFFFFFFFu) hr[j] += (uint32_t)d->rowbase;
       E.max_footprint = std::max(E.max_footprint, ggk::tile_footprint(t.blob_bytes, t.npts, t.nhalo));
-      E.flux_smem = std::max(E.flux_smem, ggk::flux_footprint(t.blob_bytes, t.npts, t.nhalo));
+      E.flux_smem = std::max(E.flux_smem, ggk::flux_footprint(t.blob_bytes, t.halo_off, t.npts, t.nhalo));
       E.h_tiles[(size_t)(k < s.nboundary ? tb++ : ti++)] = t;
     }
     E.point_of_row[i].assign((size_t)s.nrows, -1);

@@ -16,8 +16,8 @@
  * summed from 0 in the reference's face order.  Ghost rows of psd_flux are not defined by the reference (they are
  * accumulated into without ever being zeroed) and are not written.
  *
- * One CTA per tile, two or more CTAs per SM.  The tile blob (normals, halo row list, ELL adjacency) arrives by one
- * TMA bulk copy; the first 72 bytes (grad[p][0..2][0..2]) of the grad rows of the tile's own and halo points are
+ * One CTA per tile, two CTAs per SM.  The normals and the ELL adjacency of the tile blob arrive by two TMA bulk
+ * copies; the first 72 bytes (grad[p][0..2][0..2]) of the grad rows of the tile's own and halo points are
  * gathered with 8-byte cp.async.  One thread per own point walks its ELL column; nothing is written to shared
  * memory after the loads.  ELL entry: local point | ghost << 15 | face slot << 16 | (point is p1) << 31.
  * EXACT = IEEE multiply and add in the reference's expression order (bit-identical to the reference built without
@@ -32,10 +32,16 @@ namespace ggk {
 
 #define CFDP_FLUX_ROW 9 /* doubles of a grad row the flux reads: [IVX..IVZ][0..2] (flux.h:7-9) */
 
-__host__ __device__ __forceinline__ uint32_t flux_rows_off(uint32_t blob_bytes) { return (blob_bytes + 127u) & ~127u; }
-__host__ __device__ __forceinline__ uint32_t flux_footprint(uint32_t blob_bytes, uint32_t npts, uint32_t nhalo)
+/* shared memory of a tile: [normals][ELL adjacency][grad rows]; the halo row list of the blob is not staged (it is
+ * only needed to address the gather), which keeps the largest tiles below the two-CTAs-per-SM limit */
+__host__ __device__ __forceinline__ uint32_t flux_adj_src(uint32_t halo_off, uint32_t nhalo) { return halo_off + ((nhalo * 4u + 15u) & ~15u); }
+__host__ __device__ __forceinline__ uint32_t flux_rows_off(uint32_t blob_bytes, uint32_t halo_off, uint32_t nhalo)
 {
-  return flux_rows_off(blob_bytes) + (CFDP_HALO_BASE(npts) + nhalo) * (CFDP_FLUX_ROW * 8);
+  return halo_off + (blob_bytes - flux_adj_src(halo_off, nhalo)); /* multiples of 16 */
+}
+__host__ __device__ __forceinline__ uint32_t flux_footprint(uint32_t blob_bytes, uint32_t halo_off, uint32_t npts, uint32_t nhalo)
+{
+  return flux_rows_off(blob_bytes, halo_off, nhalo) + (CFDP_HALO_BASE(npts) + nhalo) * (CFDP_FLUX_ROW * 8);
 }
 
 template <bool EXACT>
@@ -80,13 +86,16 @@ psd_flux_tile_kernel(const TileDesc *__restrict__ tiles, const unsigned char *__
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int npts = td.npts, nhalo = td.nhalo, n_even = CFDP_HALO_BASE(npts);
   const unsigned char *tb = blob + td.blob;
-  double *s_rows = reinterpret_cast<double *>(smem + flux_rows_off(td.blob_bytes));
+  const uint32_t adj_src = flux_adj_src(td.halo_off, td.nhalo), adj_bytes = td.blob_bytes - adj_src;
+  double *s_rows = reinterpret_cast<double *>(smem + flux_rows_off(td.blob_bytes, td.halo_off, td.nhalo));
 
   if (tid == 0) {
     mbar_init(&full, 1);
     fence_mbar_init();
-    mbar_arrive_expect_tx(&full, td.blob_bytes);
-    bulk_g2s_hint(smem, tb, td.blob_bytes, &full, l2_policy_evict_first());
+    const uint64_t pol = l2_policy_evict_first();
+    mbar_arrive_expect_tx(&full, td.halo_off + adj_bytes);
+    if (td.halo_off) bulk_g2s_hint(smem, tb, td.halo_off, &full, pol);
+    if (adj_bytes) bulk_g2s_hint(smem + td.halo_off, tb + adj_src, adj_bytes, &full, pol);
   }
   { /* own rows: consecutive lanes = consecutive words of a row (72 of its 168 bytes) */
     const double *g = grad + (size_t)td.row0 * (NGRAD * 3);
@@ -113,7 +122,7 @@ psd_flux_tile_kernel(const TileDesc *__restrict__ tiles, const unsigned char *__
 
   if (tid < npts) {
     const double *s_nrm = reinterpret_cast<const double *>(smem);
-    const uint32_t *ell = reinterpret_cast<const uint32_t *>(smem + td.halo_off + ((nhalo * 4 + 15) & ~15)) + tid;
+    const uint32_t *ell = reinterpret_cast<const uint32_t *>(smem + td.halo_off) + tid;
     const int npad = td.npad, maxdeg = td.maxdeg;
     double a[CFDP_FLUX_ROW];
 #pragma unroll

@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--fma", action="store_true", help="fused multiply-add instead of the reference's mul+add (not bit-exact)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-flux", action="store_true", help="skip the pseudo-flux measurements")
     ap.add_argument("--cpu-mpoints", type=float, default=2.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -265,6 +266,23 @@ def main():
     S.iterate(args.variant, max(args.warmup, 3))
     barrier()
     ms_ovl = allmax(S.iterate(args.variant, args.steps) / args.steps)   # re-timed next to the bulk run (same thermal state)
+    # ---- the pseudo flux (flux.c), consumer of the exchanged gradients: its kernel alone, and the whole iteration of
+    # solver.c:45-55 (gradient + halo + pseudo flux) on the device.  Reported beside the headline, not part of it. ----
+    flux = None
+    if not args.no_flux:
+        S.flux_iterate(max(args.warmup, 3))
+        barrier()
+        ms_f = allmax(S.flux_iterate(args.steps) / args.steps)
+        S.set_flux(True)
+        S.iterate(args.variant, max(args.warmup, 3))
+        barrier()
+        ms_it = allmax(S.iterate(args.variant, args.steps) / args.steps)
+        S.set_flux(False)
+        falg = float(S.stats().flux_alg_bytes)
+        flux = dict(kernel="psd_flux_tile_kernel", kernel_ms=ms_f, alg_bytes_per_launch=int(falg), alg_bytes_per_face=falg / float(st.nfaces),
+                    achieved=falg / (ms_f * 1e-3) / 1e9, unit="GB/s", frac=falg / (ms_f * 1e-3) / 1e9 / peak,
+                    iteration_ms_grad_halo_flux=ms_it, faces_per_s_grad_halo_flux=faces_total / (ms_it * 1e-3),
+                    note="alg bytes = 32 B per face + 72 B per point (grad[p][0..2][0..2]) + 24 B per own point (psd_flux)")
     if rank == 0 and ms < 400:     # keep the GPU under the same load until the sampler has a few readings
         t_end = time.time() + 0.6
         while time.time() < t_end:
@@ -319,7 +337,7 @@ def main():
                       hidden_frac=(1.0 - max(ms_ovl - ms_k, 0.0) / (ms_bulk - ms_k)) if (world > 1 and ms_bulk > ms_k * 1.005) else None,
                       nvlink_bytes_per_iteration_per_gpu=int(st.send_rows_remote) * 168,
                       note="hidden_frac = 1 - (t_overlapped - t_comm_free) / (t_bulk_sync - t_comm_free), variant timed: " + args.variant),
-            cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
+            flux=flux, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line))
     S.close()
     if world > 1:

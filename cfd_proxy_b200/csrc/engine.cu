@@ -419,13 +419,23 @@ static void flux_prepare(void)
   CUDA_CHECK(cudaMemset(E.d_flux, 0, (size_t)E.rows * NFLUX * sizeof(double)));
   CUDA_CHECK(cudaFuncSetAttribute(ggk::psd_flux_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E.flux_smem));
   CUDA_CHECK(cudaFuncSetAttribute(ggk::psd_flux_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E.flux_smem));
+  CUDA_CHECK(cudaFuncSetAttribute(ggk::psd_flux_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E.flux_smem));
+  CUDA_CHECK(cudaFuncSetAttribute(ggk::psd_flux_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E.flux_smem));
 }
 static void launch_flux(long long tile0, long long ntiles, cudaStream_t st)
 {
   Engine &E = g_eng;
   if (ntiles <= 0) return;
   flux_prepare();
-  if (E.exact)
+  const int version = env_int("CFDP_FLUX_KERNEL", 2);
+  if (version == 2 && E.max_nhalo <= CFDP_FLUX_HALO_PER_THREAD * E.block_threads) {
+    const int chunk = std::min(E.chunk, CFDP_FLUX_MAX_CHUNK);
+    const unsigned grid = (unsigned)((ntiles + chunk - 1) / chunk);
+    if (E.exact)
+      ggk::psd_flux_pipe_kernel<true><<<grid, E.block_threads, E.flux_smem, st>>>(E.d_tiles + tile0, (int)ntiles, chunk, E.d_blob, E.d_grad, E.d_flux);
+    else
+      ggk::psd_flux_pipe_kernel<false><<<grid, E.block_threads, E.flux_smem, st>>>(E.d_tiles + tile0, (int)ntiles, chunk, E.d_blob, E.d_grad, E.d_flux);
+  } else if (E.exact)
     ggk::psd_flux_tile_kernel<true><<<(unsigned)ntiles, E.block_threads, E.flux_smem, st>>>(E.d_tiles + tile0, E.d_blob, E.d_grad, E.d_flux);
   else
     ggk::psd_flux_tile_kernel<false><<<(unsigned)ntiles, E.block_threads, E.flux_smem, st>>>(E.d_tiles + tile0, E.d_blob, E.d_grad, E.d_flux);

@@ -75,6 +75,7 @@ __device__ __forceinline__ void face_flux(const double *__restrict__ a, const do
   }
 }
 
+/* one tile per CTA (kept as a second, independent implementation: CFDP_FLUX_KERNEL=1) */
 template <bool EXACT>
 __global__ void __launch_bounds__(CFDP_MAX_TILE_POINTS, 2)
 psd_flux_tile_kernel(const TileDesc *__restrict__ tiles, const unsigned char *__restrict__ blob,
@@ -142,6 +143,136 @@ psd_flux_tile_kernel(const TileDesc *__restrict__ tiles, const unsigned char *__
     }
     double *o = flux + (size_t)(td.row0 + tid) * NFLUX;
     o[0] = ax; o[1] = ay; o[2] = az;
+  }
+}
+
+/* 72 bytes of a grad row -> shared memory in 16-byte pieces.  168 = 72 = 8 (mod 16): when the global row and its
+ * shared-memory position have the same parity, both sides are 16-byte aligned at byte 0 (even) or at byte 8 (odd). */
+__device__ __forceinline__ void flux_row_piece(double *sdst, const double *gsrc, bool odd, int k /* 0..4 */)
+{
+  if (!odd) {
+    if (k < 4) cp_async16(sdst + 2 * k, gsrc + 2 * k); else cp_async8(sdst + 8, gsrc + 8);
+  } else {
+    if (k == 0) cp_async8(sdst, gsrc); else cp_async16(sdst + 2 * k - 1, gsrc + 2 * k - 1);
+  }
+}
+
+#define CFDP_FLUX_HALO_PER_THREAD 4 /* halo rows a thread gathers: nhalo <= 4 * blockDim */
+#define CFDP_FLUX_MAX_CHUNK 16       /* tiles per CTA (descriptors in static shared memory: every byte counts against two CTAs per SM) */
+
+/*
+ * Production pseudo-flux kernel: two CTAs per SM, each walking a chunk of consecutive tiles.  Per tile:
+ *   load   thread 0 starts the two bulk copies (normals, adjacency); all threads gather the grad rows: own rows in
+ *          16-byte pieces (consecutive lanes = consecutive pieces), halo rows one row per thread from row numbers
+ *          that were fetched into registers during the previous tile's walk (no dependent global load in the way)
+ *   walk   one thread per own point; the three sums go from registers straight to global memory
+ * While one CTA of the SM loads, the other walks.
+ */
+template <bool EXACT>
+__global__ void __launch_bounds__(CFDP_MAX_TILE_POINTS, 2)
+psd_flux_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, const unsigned char *__restrict__ blob,
+                     const double *__restrict__ grad, double *__restrict__ flux)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full;
+  __shared__ TileDesc s_tds[CFDP_FLUX_MAX_CHUNK];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int t_begin = blockIdx.x * chunk;
+  const int t_end = min(t_begin + chunk, ntiles);
+  if (t_begin >= t_end) return;
+  {
+    const int nw = (t_end - t_begin) * (int)(sizeof(TileDesc) / 4);
+    const uint32_t *g = reinterpret_cast<const uint32_t *>(tiles + t_begin);
+    uint32_t *d = reinterpret_cast<uint32_t *>(s_tds);
+    for (int i = tid; i < nw; i += nthr) d[i] = __ldg(g + i);
+  }
+  if (tid == 0) {
+    mbar_init(&full, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint64_t pol = l2_policy_evict_first();
+
+  uint32_t hrow[CFDP_FLUX_HALO_PER_THREAD]; /* device rows of this thread's halo positions tid, tid + nthr, ... of the next tile to load */
+  auto fetch_halo_rows = [&](int t) {
+    if (t >= t_end) return;
+    const TileDesc pd = s_tds[t - t_begin];
+    const uint32_t *g = reinterpret_cast<const uint32_t *>(blob + pd.blob + pd.halo_off);
+#pragma unroll
+    for (int k = 0; k < CFDP_FLUX_HALO_PER_THREAD; k++) {
+      const int h = tid + k * nthr;
+      hrow[k] = h < (int)pd.nhalo ? __ldg(g + h) : 0xFFFFFFFFu;
+    }
+  };
+  fetch_halo_rows(t_begin);
+
+  for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+    const TileDesc td = s_tds[t - t_begin];
+    const int npts = td.npts, n_even = CFDP_HALO_BASE(npts);
+    const unsigned char *tb = blob + td.blob;
+    const uint32_t adj_src = flux_adj_src(td.halo_off, td.nhalo), adj_bytes = td.blob_bytes - adj_src;
+    double *s_rows = reinterpret_cast<double *>(smem + flux_rows_off(td.blob_bytes, td.halo_off, td.nhalo));
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&full, td.halo_off + adj_bytes);
+      if (td.halo_off) bulk_g2s_hint(smem, tb, td.halo_off, &full, pol);
+      if (adj_bytes) bulk_g2s_hint(smem + td.halo_off, tb + adj_src, adj_bytes, &full, pol);
+    }
+    { /* own rows: row0 is even and so is the first shared-memory row */
+      const double *g = grad + (size_t)td.row0 * (NGRAD * 3);
+      const int np = npts * 5;
+      for (int i = tid; i < np; i += nthr) {
+        const int r = i / 5, k = i - r * 5;
+        flux_row_piece(s_rows + r * CFDP_FLUX_ROW, g + (size_t)r * (NGRAD * 3), r & 1, k);
+      }
+    }
+    { /* halo rows: one row per thread */
+      double *s = s_rows + n_even * CFDP_FLUX_ROW;
+#pragma unroll
+      for (int k = 0; k < CFDP_FLUX_HALO_PER_THREAD; k++) {
+        const uint32_t row = hrow[k];
+        if (row == 0xFFFFFFFFu) continue;
+        const int h = tid + k * nthr;
+        double *sd = s + h * CFDP_FLUX_ROW;
+        const double *gs = grad + (size_t)row * (NGRAD * 3);
+        if (((row ^ (uint32_t)h) & 1u) == 0) {
+#pragma unroll
+          for (int q = 0; q < 5; q++) flux_row_piece(sd, gs, row & 1u, q);
+        } else {
+#pragma unroll
+          for (int q = 0; q < CFDP_FLUX_ROW; q++) cp_async8(sd + q, gs + q);
+        }
+      }
+    }
+    cp_async_commit();
+    fetch_halo_rows(t + 1);   /* consumed by the next iteration: the latency hides behind this tile's wait and walk */
+    cp_async_wait_all();
+    __syncthreads();                       /* everybody's rows have landed */
+    mbar_wait(&full, (uint32_t)it & 1u);   /* normals and adjacency have landed */
+
+    if (tid < npts) {
+      const double *s_nrm = reinterpret_cast<const double *>(smem);
+      const uint32_t *ell = reinterpret_cast<const uint32_t *>(smem + td.halo_off) + tid;
+      const int npad = td.npad, maxdeg = td.maxdeg;
+      double a[CFDP_FLUX_ROW];
+#pragma unroll
+      for (int k = 0; k < CFDP_FLUX_ROW; k++) a[k] = s_rows[tid * CFDP_FLUX_ROW + k];
+      double ax = 0.0, ay = 0.0, az = 0.0;
+      uint32_t e_next = maxdeg > 0 ? ell[0] : CFDP_ADJ_PAD;
+      for (int j = 0; j < maxdeg; j++) {
+        const uint32_t e = e_next;
+        e_next = j + 1 < maxdeg ? ell[(j + 1) * npad] : CFDP_ADJ_PAD;
+        if (e == CFDP_ADJ_PAD) continue;
+        const bool is_p1 = (e & 0x80000000u) != 0;
+        if (!is_p1 && !(e & 0x8000u)) continue; /* this point is p0 and p1 is an own point: flux.c:179 skips p0 (ftype 3) */
+        double fx, fy, fz;
+        face_flux<EXACT>(a, s_rows + CFDP_FLUX_ROW * (e & 0x7FFFu), s_nrm + 3 * ((e >> 16) & 0x7FFFu), fx, fy, fz);
+        if (is_p1) { fx = -fx; fy = -fy; fz = -fz; }   /* psd_flux[p1] -= flux (flux.c:185-190) */
+        ax = __dadd_rn(ax, fx); ay = __dadd_rn(ay, fy); az = __dadd_rn(az, fz);
+      }
+      double *o = flux + (size_t)(td.row0 + tid) * NFLUX;
+      o[0] = ax; o[1] = ay; o[2] = az;
+    }
+    __syncthreads(); /* shared memory is free for the next tile */
   }
 }
 

@@ -41,7 +41,10 @@ def oracle_chain(doms, exchange=True):
 
 @pytest.mark.parametrize("n,p,order,hexfrac,tile,torder", CASES)
 @pytest.mark.parametrize("variant", ["comm_free", "mpi_bulk_sync", "mpi_async", "gaspi_async"])
-def test_flux_after_gradient_and_exchange_bit_identical(session_factory, n, p, order, hexfrac, tile, torder, variant):
+@pytest.mark.parametrize("kernel", [2, 1])   # 2 = chunked kernel with prefetched halo row numbers (production), 1 = one tile per CTA
+def test_flux_after_gradient_and_exchange_bit_identical(session_factory, monkeypatch, n, p, order, hexfrac, tile, torder, variant, kernel):
+    monkeypatch.setenv("CFDP_FLUX_KERNEL", str(kernel))
+    monkeypatch.setenv("CFDP_CHUNK", "3")
     spec = M.make_spec(n, p, order=order, brick=4, hexfrac=hexfrac)
     nd = p[0] * p[1] * p[2]
     doms = [M.gen_domain(spec, r) for r in range(nd)]

@@ -230,9 +230,17 @@ def test_reference_main_runs_on_the_library(tmp_path):
     # var == 1.0 (init_solver_data, solver_data.c:26-36): checksum of the oracle's gradients on the same mesh
     d = doms[0]
     g = O.gradients(d, np.ones((d["nall"], 7)), order=1)
-    line = [l for l in r.stdout.splitlines() if "CHECKSUM" in l][0]
+    line = [l for l in r.stdout.splitlines() if "CHECKSUM (rank" in l][0]
     got = float(line.split(":")[1])
     want = 0.0
     for v in g[:d["nown"]].ravel():
+        want += v
+    assert got == want
+    # ... and of the pseudo flux computed from them (solver.c:52, flux.c)
+    fl = O.psd_flux(d, g, order=1)
+    line = [l for l in r.stdout.splitlines() if "CHECKSUM psd_flux" in l][0]
+    got = float(line.split(":")[1])
+    want = 0.0
+    for v in fl[:d["nown"]].ravel():
         want += v
     assert got == want

@@ -1,8 +1,8 @@
 /*
  * test_solver_b200.c -- the benchmark loop the reference's main() calls (reference src/solver.c:35-314),
  * re-written for the B200 library: same protocol (N_MEDIAN = 25 repeats of NITER iterations per variant,
- * median reported), same "*** SETUP / *** TIMINGS" print format, gradient + halo exchange only (the
- * pseudo-flux of solver.c:50 is outside this path).  Compiled against the REFERENCE headers: the structs
+ * median reported), same "*** SETUP / *** TIMINGS" print format, every iteration = gradient + halo exchange
+ * followed by the pseudo flux (solver.c:45-55).  Compiled against the REFERENCE headers: the structs
  * it passes to libcfdp_b200.so are the reference's own comm_data / solver_data.
  * Built by `make -C oracle dropin` together with the unmodified src/hybrid.f6.c.
  */
@@ -12,6 +12,7 @@
 #include "comm_data.h"
 #include "solver_data.h"
 #include "gradients.h"
+#include "flux.h"
 #include "exchange_data_mpi.h"
 #include "solver.h"
 
@@ -19,6 +20,7 @@ void cfdp_set_resident(int resident);
 void cfdp_device_synchronize(void);
 void cfdp_var_to_device(solver_data *sd);
 void cfdp_grad_to_host(solver_data *sd);
+void cfdp_flux_to_host(solver_data *sd);
 
 #define N_MEDIAN 25
 #define N_SOLVER 10
@@ -54,7 +56,10 @@ void test_solver(comm_data *cd, solver_data *sd, int NTHREADS)
       cfdp_device_synchronize();
       double t = -now_s();
       if (v == 2 || v == 3) exchange_dbl_mpi_post_recv(cd, NGRAD * 3);    /* solver.c:87,106 */
-      for (i = 0; i < sd->niter; ++i) fn[v](cd, sd, i == sd->niter - 1);
+      for (i = 0; i < sd->niter; ++i) {
+        fn[v](cd, sd, i == sd->niter - 1);
+        compute_psd_flux(sd);                                             /* solver.c:52 */
+      }
       cfdp_device_synchronize();
       t += now_s();
       median[v][k] = t;
@@ -63,6 +68,7 @@ void test_solver(comm_data *cd, solver_data *sd, int NTHREADS)
   }
   cfdp_set_resident(0);
   cfdp_grad_to_host(sd);
+  cfdp_flux_to_host(sd);
   if (cd->iProc == 0) {
     printf("\n*** COMPILE FLAGS\n -DCFDP_B200 (sm_100a CUDA kernels, NCCL halo exchange)");
     printf("\n\n*** SETUP\n");
@@ -86,5 +92,8 @@ void test_solver(comm_data *cd, solver_data *sd, int NTHREADS)
     double s = 0.0;
     for (i = 0; i < sd->nownpoints; i++) for (v = 0; v < NGRAD; v++) for (k = 0; k < 3; k++) s += sd->grad[i][v][k];
     printf("\n*** CHECKSUM (rank 0 own rows): %.17g\n", s);
+    s = 0.0;
+    for (i = 0; i < sd->nownpoints; i++) for (k = 0; k < NFLUX; k++) s += sd->psd_flux[i][k];
+    printf("*** CHECKSUM psd_flux (rank 0 own rows): %.17g\n", s);
   }
 }

@@ -1,5 +1,6 @@
 """Worker of tests/test_multigpu.py: one torchrun rank per GPU (NCCL).  Every rank checks its hosted
-domains -- own rows AND ghost rows filled over NVLink -- bit for bit against the oracle."""
+domains -- own rows AND ghost rows filled over NVLink -- bit for bit against the oracle, and the pseudo flux
+(flux.c) computed from those exchanged rows."""
 import json
 import os
 import sys
@@ -24,6 +25,7 @@ def main():
     recv, send = O.recvsend_index(doms)
     want = [O.gradients(d, M.var_for(d), is_send=O.is_send_mask(d, send[a]), order=1) for a, d in enumerate(doms)]
     want = O.exchange(want, recv, send)
+    want_flux = [O.psd_flux(d, want[a], is_send=O.is_send_mask(d, send[a]), order=1) for a, d in enumerate(doms)]
     S = session_from_env(nd, backend="nccl")
     S.load_spec(spec)
     S.setup()
@@ -31,13 +33,20 @@ def main():
     for variant in ("mpi_bulk_sync", "mpi_early_recv", "mpi_async", "gaspi_bulk_sync", "gaspi_async"):  # gaspi_* = CUDA-IPC put + notify
         for d in S.domains:
             d.grad[:] = np.nan
+            d.psd_flux[:] = np.nan
         S.lib.cfdp_set_resident(1)
+        S.set_flux(True)                 # every iteration: gradient + exchange, then the pseudo flux on the exchanged rows
         S.iterate(variant, 3)
         S.download_grad()
+        S.download_flux()
         for d in S.domains:
             bad = int((d.grad.view(np.uint64) != want[d.rank].view(np.uint64)).sum())
             if bad:
                 errors.append(f"{variant}: domain {d.rank}: {bad} words differ")
+            nown = doms[d.rank]["nown"]
+            bad = int((d.psd_flux[:nown].view(np.uint64) != want_flux[d.rank][:nown].view(np.uint64)).sum())
+            if bad:
+                errors.append(f"{variant}: domain {d.rank}: {bad} pseudo-flux words differ")
     st = S.stats()
     out = dict(rank=S.proc_rank, errors=errors, local=int(st.send_rows_local), remote=int(st.send_rows_remote))
     with open(os.path.join(os.environ["CFDP_MP_OUT"], f"rank{S.proc_rank}.json"), "w") as f:

@@ -279,7 +279,7 @@ def main():
         ms_it = allmax(S.iterate(args.variant, args.steps) / args.steps)
         S.set_flux(False)
         falg = float(S.stats().flux_alg_bytes)
-        flux = dict(kernel="psd_flux_tile_kernel", kernel_ms=ms_f, alg_bytes_per_launch=int(falg), alg_bytes_per_face=falg / float(st.nfaces),
+        flux = dict(kernel="psd_flux_pipe_kernel" if int(os.environ.get("CFDP_FLUX_KERNEL", "2")) == 2 else "psd_flux_tile_kernel", kernel_ms=ms_f, alg_bytes_per_launch=int(falg), alg_bytes_per_face=falg / float(st.nfaces),
                     achieved=falg / (ms_f * 1e-3) / 1e9, unit="GB/s", frac=falg / (ms_f * 1e-3) / 1e9 / peak,
                     iteration_ms_grad_halo_flux=ms_it, faces_per_s_grad_halo_flux=faces_total / (ms_it * 1e-3),
                     note="alg bytes = 32 B per face + 72 B per point (grad[p][0..2][0..2]) + 24 B per own point (psd_flux)")

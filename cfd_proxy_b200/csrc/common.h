@@ -68,6 +68,12 @@ struct DomainSchedule {
   std::vector<long long> tile_face_off; /* [ntiles+1] */
   std::vector<int> tile_halo_pts;       /* concatenated original local point ids */
   std::vector<long long> tile_halo_off; /* [ntiles+1] */
+  /* pseudo flux (flux.c): per tile a second, smaller blob in the same format -- only the adjacency entries that
+   * contribute (this point is p1 of the face, or p0 with a ghost p1), the normals of those faces (every face once
+   * per domain instead of once per incident tile) and the halo rows those entries reference */
+  std::vector<unsigned char> fblob;
+  std::vector<uint64_t> ftile_blob;     /* [ntiles+1] */
+  std::vector<int> ftile_nfaces, ftile_nhalo, ftile_maxdeg;
   int max_nfaces = 0, max_nloc = 0;     /* per-tile maxima: faces, local points (own, even-padded, + halo) */
   size_t max_blob = 0;                  /* largest tile blob in bytes */
   long long lds_wavefronts_min = 0, lds_wavefronts_est = 0; /* face-walk shared-memory wavefronts: conflict free / estimated */
@@ -80,6 +86,7 @@ struct ScheduleOptions {
   int order;           /* 0 = greedy graph growing, 1 = consecutive chunks of the file numbering */
   int bank_placement;  /* 1 = place face slots and halo rows by shared-memory bank (fewer conflicts), 0 = discovery order */
   int slack_slots, slack_halo; /* spare face slots / halo positions per tile for the bank placement */
+  int flux_blob;       /* 1 = also build the pseudo-flux blobs */
   int sort_in_tile;    /* 1 = points of a tile in ascending file numbering, 0 = in growth (BFS) order */
   int stage_budget;    /* bytes one tile may occupy in shared memory (blob + var rows + volumes); 0 = no limit */
 };

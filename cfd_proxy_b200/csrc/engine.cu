@@ -112,6 +112,7 @@ struct Engine {
   /* device */
   long long rows = 0, ntiles = 0, nbtiles = 0;
   double *d_var = nullptr, *d_grad = nullptr, *d_pvol = nullptr;
+  unsigned char *d_fblob = nullptr; TileDesc *d_ftiles = nullptr; std::vector<TileDesc> h_ftiles; std::vector<size_t> fblob_base; size_t fblob_bytes = 0; /* pseudo-flux blobs (same tile order as h_tiles) */
   double *d_flux = nullptr; int with_flux = 0; uint32_t flux_smem = 0; double last_flux_ms = 0; long long flux_alg_bytes = 0; /* pseudo flux (flux.c), lazily allocated */
   unsigned char *d_blob = nullptr;
   TileDesc *d_tiles = nullptr;
@@ -237,6 +238,7 @@ extern "C" int cfdp_configure(int proc_rank, int nprocs, int ndomains_total, int
   }
   E.sopt.order = env_int("CFDP_TILE_ORDER", 0);
   E.sopt.sort_in_tile = env_int("CFDP_SORT_IN_TILE", 1);
+  E.sopt.flux_blob = env_int("CFDP_FLUX_BLOB", 1);
   E.sopt.bank_placement = env_int("CFDP_BANK_PLACEMENT", 1);
   E.sopt.slack_slots = env_int("CFDP_SLACK_SLOTS", 0);
   E.sopt.slack_halo = env_int("CFDP_SLACK_HALO", 0);
@@ -428,17 +430,19 @@ static void launch_flux(long long tile0, long long ntiles, cudaStream_t st)
   if (ntiles <= 0) return;
   flux_prepare();
   const int version = env_int("CFDP_FLUX_KERNEL", 2);
+  const TileDesc *tiles = E.d_ftiles ? E.d_ftiles : E.d_tiles;
+  const unsigned char *blob = E.d_ftiles ? E.d_fblob : E.d_blob;
   if (version == 2 && E.max_nhalo <= CFDP_FLUX_HALO_PER_THREAD * E.block_threads) {
     const int chunk = std::min(E.chunk, CFDP_FLUX_MAX_CHUNK);
     const unsigned grid = (unsigned)((ntiles + chunk - 1) / chunk);
     if (E.exact)
-      ggk::psd_flux_pipe_kernel<true><<<grid, E.block_threads, E.flux_smem, st>>>(E.d_tiles + tile0, (int)ntiles, chunk, E.d_blob, E.d_grad, E.d_flux);
+      ggk::psd_flux_pipe_kernel<true><<<grid, E.block_threads, E.flux_smem, st>>>(tiles + tile0, (int)ntiles, chunk, blob, E.d_grad, E.d_flux);
     else
-      ggk::psd_flux_pipe_kernel<false><<<grid, E.block_threads, E.flux_smem, st>>>(E.d_tiles + tile0, (int)ntiles, chunk, E.d_blob, E.d_grad, E.d_flux);
+      ggk::psd_flux_pipe_kernel<false><<<grid, E.block_threads, E.flux_smem, st>>>(tiles + tile0, (int)ntiles, chunk, blob, E.d_grad, E.d_flux);
   } else if (E.exact)
-    ggk::psd_flux_tile_kernel<true><<<(unsigned)ntiles, E.block_threads, E.flux_smem, st>>>(E.d_tiles + tile0, E.d_blob, E.d_grad, E.d_flux);
+    ggk::psd_flux_tile_kernel<true><<<(unsigned)ntiles, E.block_threads, E.flux_smem, st>>>(tiles + tile0, blob, E.d_grad, E.d_flux);
   else
-    ggk::psd_flux_tile_kernel<false><<<(unsigned)ntiles, E.block_threads, E.flux_smem, st>>>(E.d_tiles + tile0, E.d_blob, E.d_grad, E.d_flux);
+    ggk::psd_flux_tile_kernel<false><<<(unsigned)ntiles, E.block_threads, E.flux_smem, st>>>(tiles + tile0, blob, E.d_grad, E.d_flux);
   CUDA_CHECK(cudaGetLastError());
   E.launches++;
 }
@@ -493,6 +497,9 @@ extern "C" void cfdp_plan(void)
   E.h_tiles.resize((size_t)E.ntiles);
   E.blob_base.resize((size_t)nh);
   for (int i = 0; i < nh; i++) { E.blob_base[i] = E.blob_bytes; E.blob_bytes += E.doms[i]->sch.blob.size(); }
+  const bool fb = E.sopt.flux_blob != 0;
+  E.h_ftiles.assign(fb ? (size_t)E.ntiles : 0, TileDesc{}); E.fblob_base.assign((size_t)nh, 0); E.fblob_bytes = 0;
+  for (int i = 0; i < nh; i++) { E.fblob_base[i] = E.fblob_bytes; E.fblob_bytes += E.doms[i]->sch.fblob.size(); }
   long long tb = 0, ti = E.nbtiles;
   E.point_of_row.resize((size_t)nh);
   for (int i = 0; i < nh; i++) {
@@ -511,8 +518,21 @@ extern "C" void cfdp_plan(void)
       uint32_t *hr = (uint32_t *)(&s.blob[s.tile_blob[k]] + t.halo_off);
       for (int j = 0; j < s.tile_nhpos[k]; j++) if (hr[j] != 0xFFFFFFFFu) hr[j] += (uint32_t)d->rowbase;
       E.max_footprint = std::max(E.max_footprint, ggk::tile_footprint(t.blob_bytes, t.npts, t.nhalo));
-      E.flux_smem = std::max(E.flux_smem, ggk::flux_footprint(t.blob_bytes, t.halo_off, t.npts, t.nhalo));
-      E.h_tiles[(size_t)(k < s.nboundary ? tb++ : ti++)] = t;
+      const size_t slot = (size_t)(k < s.nboundary ? tb++ : ti++);
+      E.h_tiles[slot] = t;
+      if (fb) { /* the tile's pseudo-flux blob: same format, fewer faces / halo rows / adjacency rows */
+        TileDesc f = t;
+        f.nhalo = (uint16_t)s.ftile_nhalo[k]; f.nfaces = (uint32_t)s.ftile_nfaces[k]; f.maxdeg = (uint16_t)s.ftile_maxdeg[k];
+        f.blob = (uint64_t)(E.fblob_base[i] + s.ftile_blob[k]);
+        f.blob_bytes = (uint32_t)(s.ftile_blob[(size_t)k + 1] - s.ftile_blob[k]);
+        f.halo_off = (uint32_t)blob_halo_off(f.nfaces);
+        uint32_t *fh = (uint32_t *)(&s.fblob[s.ftile_blob[k]] + f.halo_off);
+        for (int j = 0; j < s.ftile_nhalo[k]; j++) if (fh[j] != 0xFFFFFFFFu) fh[j] += (uint32_t)d->rowbase;
+        E.h_ftiles[slot] = f;
+        E.flux_smem = std::max(E.flux_smem, ggk::flux_footprint(f.blob_bytes, f.halo_off, f.npts, f.nhalo));
+      } else {
+        E.flux_smem = std::max(E.flux_smem, ggk::flux_footprint(t.blob_bytes, t.halo_off, t.npts, t.nhalo));
+      }
     }
     E.point_of_row[i].assign((size_t)s.nrows, -1);
     for (int p = 0; p < s.nall; p++) E.point_of_row[i][(size_t)s.row_of_point[p]] = p;
@@ -618,6 +638,15 @@ extern "C" void cfdp_commit(void)
     std::vector<unsigned char>().swap(s.blob); /* the host copy is not needed any more */
   }
   E.d_tiles = upload(E.h_tiles);
+  if (E.sopt.flux_blob) {
+    CUDA_CHECK(cudaMalloc(&E.d_fblob, E.fblob_bytes ? E.fblob_bytes : 16));
+    for (int i = 0; i < nh; i++) {
+      DomainSchedule &s = E.doms[i]->sch;
+      CUDA_CHECK(cudaMemcpy(E.d_fblob + E.fblob_base[i], s.fblob.data(), s.fblob.size(), cudaMemcpyHostToDevice));
+      std::vector<unsigned char>().swap(s.fblob);
+    }
+    E.d_ftiles = upload(E.h_ftiles);
+  }
 
   CUDA_CHECK(cudaMalloc(&E.d_var, (size_t)E.rows * NGRAD * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&E.d_grad, (size_t)E.rows * CFDP_DIM2 * sizeof(double)));
@@ -1202,7 +1231,7 @@ extern "C" void cfdp_get_stats(cfdp_stats *st)
   st->alg_bytes = E.alg_bytes; st->h2d_bytes = E.nall * NGRAD * 8; st->d2h_bytes = E.nall * CFDP_DIM2 * 8;
   for (Domain *d : E.doms) { st->lds_wavefronts_min += d->sch.lds_wavefronts_min; st->lds_wavefronts_est += d->sch.lds_wavefronts_est; }
   st->launches = E.launches; st->last_kernel_ms = E.last_kernel_ms; st->smem_bytes = E.smem_bytes;
-  st->flux_alg_bytes = E.flux_alg_bytes; st->last_flux_ms = E.last_flux_ms; st->flux_smem_bytes = (int)E.flux_smem;
+  st->flux_alg_bytes = E.flux_alg_bytes; st->last_flux_ms = E.last_flux_ms; st->flux_smem_bytes = (int)E.flux_smem; st->flux_blob_bytes = (long long)E.fblob_bytes;
 }
 
 extern "C" int cfdp_get_schedule(const solver_data *sd, cfdp_schedule_view *v)
@@ -1323,7 +1352,7 @@ extern "C" void cfdp_finalize(void)
   if (E.have_device) {
     cudaDeviceSynchronize();
     if (E.comm) { g_nccl.CommDestroy(E.comm); E.comm = nullptr; }
-    cudaFree(E.d_var); cudaFree(E.d_grad); cudaFree(E.d_pvol); cudaFree(E.d_flux); E.d_flux = nullptr; cudaFree(E.d_blob); cudaFree(E.d_tiles); cudaFree(E.d_stage);
+    cudaFree(E.d_var); cudaFree(E.d_grad); cudaFree(E.d_pvol); cudaFree(E.d_flux); E.d_flux = nullptr; cudaFree(E.d_fblob); cudaFree(E.d_ftiles); E.d_fblob = nullptr; E.d_ftiles = nullptr; cudaFree(E.d_blob); cudaFree(E.d_tiles); cudaFree(E.d_stage);
     cudaFree(E.d_loc_dst); cudaFree(E.d_loc_src); cudaFree(E.d_exp_off); cudaFree(E.d_exp_src); cudaFree(E.d_exp_dst); cudaFree(E.d_send_rows); cudaFree(E.d_recv_rows); cudaFree(E.d_sendbuf); cudaFree(E.d_recvbuf);
     for (int *p : E.d_rowmap) cudaFree(p);
   }
@@ -1359,7 +1388,7 @@ extern "C" void cfdp_finalize(void)
   E.committed = false; E.planned = false; E.configured = false;
   E.h_exp_off.clear(); E.h_exp_src.clear(); E.h_exp_dst.clear(); E.d_exp_off = E.d_exp_src = E.d_exp_dst = nullptr;
   E.h_tiles.clear(); E.blob_base.clear(); E.h_loc_dst.clear(); E.h_loc_src.clear(); E.h_send_rows.clear(); E.h_recv_rows.clear();
-  E.max_nfaces = E.max_nloc = E.max_npts = 0; E.max_stage = 0; E.blob_bytes = 0; E.max_blob = 0; E.max_nhalo = 0; E.max_footprint = 0; E.flux_smem = 0; E.with_flux = 0; E.flux_alg_bytes = 0;
+  E.max_nfaces = E.max_nloc = E.max_npts = 0; E.max_stage = 0; E.blob_bytes = 0; E.max_blob = 0; E.max_nhalo = 0; E.max_footprint = 0; E.flux_smem = 0; E.with_flux = 0; E.flux_alg_bytes = 0; E.h_ftiles.clear(); E.fblob_bytes = 0;
   E.rows = E.ntiles = E.nbtiles = 0; E.nfaces = E.nown = E.nall = E.tile_faces = E.halo_refs = E.alg_bytes = 0;
   E.n_local = E.n_send = E.n_recv = 0; E.launches = 0; E.nprocs = 0; E.per_proc = 0;
 }

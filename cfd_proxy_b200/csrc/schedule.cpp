@@ -415,6 +415,8 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
 
   /* pass B: order every point's faces, place face slots and halo rows by shared-memory bank, emit blobs */
   const bool place_by_bank = opt.bank_placement != 0;
+  std::vector<std::vector<unsigned char>> ftile_bytes(opt.flux_blob ? (size_t)ntiles : 0);
+  out.ftile_nfaces.assign(opt.flux_blob ? (size_t)ntiles : 0, 0); out.ftile_nhalo = out.ftile_nfaces; out.ftile_maxdeg = out.ftile_nfaces;
   long long wf_min_total = 0, wf_est_total = 0;
 #pragma omp parallel reduction(+ : wf_min_total, wf_est_total)
   {
@@ -424,6 +426,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
     std::vector<int> deg, slot_of, hpos_of;      /* fid -> slot, halo k -> position */
     std::vector<unsigned char> cntv, cntn;       /* [group][16] */
     std::vector<int> grp_off, grp_list;          /* per face / per halo point: distinct groups */
+    std::vector<int> inv_slot, inv_hpos, fslot_of, fhpos_of; /* pseudo-flux blob */
 #pragma omp for schedule(dynamic, 16)
     for (int k = 0; k < ntiles; k++) {
       const int n = out.tile_npts[k], nf = out.tile_nfaces[k], nh = tnh[k], md = tmaxdeg[k];
@@ -577,6 +580,53 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
           ell[(size_t)j * npad + i] = loc | ghost | ((uint32_t)slot_of[e.fid] << 16) | (e.sign << 31);
         }
 
+      /* ---- the pseudo-flux blob of the tile (flux.c:179-190 with one thread): an own point receives -flux from the
+       * faces where it is p1 and +flux from the faces where it is p0 and p1 is a ghost; nothing else is stored.
+       * Slots and halo positions keep the relative order of the gradient blob. */
+      if (opt.flux_blob) {
+        auto contributes = [&](const Ent &e) { return e.sign != 0 || (e.nbr >= n && hpts[e.nbr - n] >= nown); };
+        inv_slot.assign((size_t)nslots, -1); inv_hpos.assign((size_t)nhpos, -1);
+        for (int f = 0; f < nf; f++) inv_slot[slot_of[f]] = f;
+        for (int h = 0; h < nh; h++) inv_hpos[hpos_of[h]] = h;
+        fslot_of.assign((size_t)nf, -1); fhpos_of.assign((size_t)nh, -1);
+        int fmd = 0;
+        for (int i = 0; i < n; i++) {
+          int c = 0;
+          for (int j = 0; j < deg[i]; j++) {
+            const Ent &e = tile_ents[(size_t)i * md + j];
+            if (!contributes(e)) continue;
+            c++; fslot_of[e.fid] = 0;
+            if (e.nbr >= n) fhpos_of[e.nbr - n] = 0;
+          }
+          fmd = std::max(fmd, c);
+        }
+        int nff = 0, nfh = 0;
+        for (int sl = 0; sl < nslots; sl++) if (inv_slot[sl] >= 0 && fslot_of[inv_slot[sl]] == 0) fslot_of[inv_slot[sl]] = nff++;
+        for (int hp = 0; hp < nhpos; hp++) if (inv_hpos[hp] >= 0 && fhpos_of[inv_hpos[hp]] == 0) fhpos_of[inv_hpos[hp]] = nfh++;
+        std::vector<unsigned char> &fb = ftile_bytes[k];
+        fb.assign(blob_size((uint32_t)nff, (uint32_t)nfh, (uint32_t)fmd, npad), 0);
+        double *fn = (double *)fb.data();
+        uint32_t *fh = (uint32_t *)(fb.data() + blob_halo_off((uint32_t)nff));
+        uint32_t *fe = (uint32_t *)(fb.data() + blob_adj_off((uint32_t)nff, (uint32_t)nfh));
+        for (size_t i = 0; i < (size_t)fmd * npad; i++) fe[i] = CFDP_ADJ_PAD;
+        for (int j = 0; j < (int)(align_up((size_t)nfh * 4, 16) / 4); j++) fh[j] = 0xFFFFFFFFu;
+        for (int f = 0; f < nf; f++)
+          if (fslot_of[f] >= 0) { const int gf = fids[f], sl = fslot_of[f]; fn[3 * sl] = sd->fnormal[gf][0]; fn[3 * sl + 1] = sd->fnormal[gf][1]; fn[3 * sl + 2] = sd->fnormal[gf][2]; }
+        for (int h = 0; h < nh; h++) if (fhpos_of[h] >= 0) fh[fhpos_of[h]] = (uint32_t)out.row_of_point[hpts[h]];
+        for (int i = 0; i < n; i++) {
+          int c = 0;
+          for (int j = 0; j < deg[i]; j++) {
+            const Ent &e = tile_ents[(size_t)i * md + j];
+            if (!contributes(e)) continue;
+            const uint32_t loc = e.nbr < n ? (uint32_t)e.nbr : (uint32_t)(n_even + fhpos_of[e.nbr - n]);
+            const uint32_t ghost = (e.nbr >= n && hpts[e.nbr - n] >= nown) ? 0x8000u : 0u;
+            fe[(size_t)c * npad + i] = loc | ghost | ((uint32_t)fslot_of[e.fid] << 16) | (e.sign << 31);
+            c++;
+          }
+        }
+        out.ftile_nfaces[k] = nff; out.ftile_nhalo[k] = nfh; out.ftile_maxdeg[k] = fmd;
+      }
+
       /* shared-memory wavefront estimate of the face walk: 7 var words + 3 normal words per face end */
       for (int w0 = 0; w0 < n; w0 += 16)
         for (int j = 0; j < md; j++) {
@@ -604,4 +654,14 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
     }
   }
   out.lds_wavefronts_min = wf_min_total; out.lds_wavefronts_est = wf_est_total;
+  if (opt.flux_blob) {
+    out.ftile_blob.assign((size_t)ntiles + 1, 0);
+    for (int k = 0; k < ntiles; k++) out.ftile_blob[(size_t)k + 1] = out.ftile_blob[k] + ftile_bytes[k].size();
+    out.fblob.resize((size_t)out.ftile_blob[ntiles]);
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < ntiles; k++) {
+      if (!ftile_bytes[k].empty()) memcpy(&out.fblob[out.ftile_blob[k]], ftile_bytes[k].data(), ftile_bytes[k].size());
+      std::vector<unsigned char>().swap(ftile_bytes[k]);
+    }
+  }
 }

@@ -89,7 +89,7 @@ class Stats(C.Structure):
         ("last_kernel_ms", C.c_double),
         ("nprocs", C.c_int), ("proc_rank", C.c_int), ("ndomains_hosted", C.c_int),
         ("tile_points", C.c_int), ("smem_bytes", C.c_int), ("flux_smem_bytes", C.c_int),
-        ("flux_alg_bytes", C.c_longlong), ("last_flux_ms", C.c_double),
+        ("flux_alg_bytes", C.c_longlong), ("last_flux_ms", C.c_double), ("flux_blob_bytes", C.c_longlong),
     ]
 
 

@@ -228,6 +228,7 @@ typedef struct {
   int flux_smem_bytes;       /* shared memory per CTA of the pseudo-flux kernel */
   long long flux_alg_bytes;  /* algorithmic bytes of one pseudo-flux pass: 32 B per face + 72 B per point + 24 B per own point */
   double last_flux_ms;       /* mean device time of one pseudo-flux pass in the last cfdp_flux_iterate */
+  long long flux_blob_bytes; /* size of the pseudo-flux tile blobs (0: the kernel reads the gradient blobs) */
 } cfdp_stats;
 void cfdp_get_stats(cfdp_stats *st);
 

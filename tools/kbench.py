@@ -50,7 +50,7 @@ def main():
                 prof = dict(wait=round(buf[0] / nt), walk=round(buf[1] / nt), rest=round(buf[2] / nt), stage_S2=round(buf[5] / nt), store_exports_earlyfetch=round(buf[6] / nt), wait_read=round(buf[7] / nt))
                 print("  phase cycles per tile (thread 0):", prof, flush=True)
             print(json.dumps(dict(cfg=cfg, kernel_ms=round(ms, 4), gfaces=round(st.nfaces / ms / 1e6, 2), frac=round(st.alg_bytes / ms / 1e6 / peak, 4),
-                                  async_ms=round(ms_a, 4), flux_ms=round(ms_f, 4), flux_frac=round(st.flux_alg_bytes / ms_f / 1e6 / peak, 4), flux_smem=st.flux_smem_bytes, smem=st.smem_bytes, tiles=st.ntiles, dup=round(st.tile_faces / st.nfaces, 3),
+                                  async_ms=round(ms_a, 4), flux_ms=round(ms_f, 4), flux_frac=round(st.flux_alg_bytes / ms_f / 1e6 / peak, 4), flux_smem=st.flux_smem_bytes, flux_blob_B_per_face=round(st.flux_blob_bytes / st.nfaces, 2), smem=st.smem_bytes, tiles=st.ntiles, dup=round(st.tile_faces / st.nfaces, 3),
                                   blob_B_per_face=round(st.blob_bytes / st.nfaces, 2), setup_s=round(time.time() - t0, 1))), flush=True)
 
 if __name__ == "__main__":

@@ -426,7 +426,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
     std::vector<int> deg, slot_of, hpos_of;      /* fid -> slot, halo k -> position */
     std::vector<unsigned char> cntv, cntn;       /* [group][16] */
     std::vector<int> grp_off, grp_list;          /* per face / per halo point: distinct groups */
-    std::vector<int> inv_slot, inv_hpos, fslot_of, fhpos_of; /* pseudo-flux blob */
+    std::vector<Ent> ftile_ents; std::vector<int> fdeg, fface_of, fhalo_of, fslot_of, fhpos_of; std::vector<unsigned char> fghost; /* pseudo-flux blob */
 #pragma omp for schedule(dynamic, 16)
     for (int k = 0; k < ntiles; k++) {
       const int n = out.tile_npts[k], nf = out.tile_nfaces[k], nh = tnh[k], md = tmaxdeg[k];
@@ -490,22 +490,25 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
        * words of the same bank pair.  Row r / slot s sits in bank-pair class r mod 16 / s mod 16 (row and slot
        * strides are 7 and 3 words, both odd).  Own rows are fixed by the tile order; halo rows and face slots
        * are free: greedily give each the class that adds the fewest collisions over the groups it is read in. */
-      slot_of.assign((size_t)nf, -1); hpos_of.assign((size_t)nh, -1);
-      const int nhw = (n + 15) / 16, ngrp = nhw * md;
+      /* the placement, for an adjacency given as (E_[i*MD + j], D_[i]): nH halo points -> HP (NHP positions), nF faces -> SL (NSL slots) */
+      auto place_all = [&](const std::vector<Ent> &E_, const std::vector<int> &D_, int MD, int nH, int nF,
+                           std::vector<int> &HP, int NHP, std::vector<int> &SL, int NSL) {
+      SL.assign((size_t)nF, -1); HP.assign((size_t)nH, -1);
+      const int nhw = (n + 15) / 16, ngrp = nhw * MD;
       if (!place_by_bank) {
-        for (int f = 0; f < nf; f++) slot_of[f] = f;
-        for (int h = 0; h < nh; h++) hpos_of[h] = h;
+        for (int f = 0; f < nF; f++) SL[f] = f;
+        for (int h = 0; h < nH; h++) HP[h] = h;
       } else {
         cntv.assign((size_t)ngrp * 16, 0); cntn.assign((size_t)ngrp * 16, 0);
         /* own rows: distinct rows per group */
         for (int hw = 0; hw < nhw; hw++)
-          for (int j = 0; j < md; j++) {
-            unsigned char *cv = &cntv[((size_t)hw * md + j) * 16];
+          for (int j = 0; j < MD; j++) {
+            unsigned char *cv = &cntv[((size_t)hw * MD + j) * 16];
             int seen[16], ns = 0;
             for (int l = 0; l < 16; l++) {
               const int i = hw * 16 + l;
-              if (i >= n || j >= deg[i]) continue;
-              const int r = tile_ents[(size_t)i * md + j].nbr;
+              if (i >= n || j >= D_[i]) continue;
+              const int r = E_[(size_t)i * MD + j].nbr;
               if (r >= n) continue;
               bool dup = false;
               for (int t = 0; t < ns; t++) if (seen[t] == r) dup = true;
@@ -521,10 +524,10 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
             std::vector<int> fill;
             if (pass == 1) fill.assign(grp_off.begin(), grp_off.end() - 1);
             for (int i = 0; i < n; i++)
-              for (int j = 0; j < deg[i]; j++) {
-                const int o = obj_of(tile_ents[(size_t)i * md + j]);
+              for (int j = 0; j < D_[i]; j++) {
+                const int o = obj_of(E_[(size_t)i * MD + j]);
                 if (o < 0) continue;
-                const int gidx = (i / 16) * md + j;
+                const int gidx = (i / 16) * MD + j;
                 if (pass == 0) grp_off[(size_t)o + 1]++;
                 else {
                   bool dup = false;
@@ -560,9 +563,11 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
             used[best]++;
           }
         };
-        place(nh, false, cntv, hpos_of, nhpos, n_even & 15);
-        place(nf, true, cntn, slot_of, nslots, 0);
+        place(nH, false, cntv, HP, NHP, n_even & 15);
+        place(nF, true, cntn, SL, NSL, 0);
       }
+      };
+      place_all(tile_ents, deg, md, nh, nf, hpos_of, nhpos, slot_of, nslots);
 
       /* ---- emit */
       for (int f = 0; f < nf; f++) {
@@ -582,49 +587,61 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
 
       /* ---- the pseudo-flux blob of the tile (flux.c:179-190 with one thread): an own point receives -flux from the
        * faces where it is p1 and +flux from the faces where it is p0 and p1 is a ghost; nothing else is stored.
-       * Slots and halo positions keep the relative order of the gradient blob. */
+       * Face slots and halo positions are placed by bank for this adjacency like those of the gradient blob. */
       if (opt.flux_blob) {
         auto contributes = [&](const Ent &e) { return e.sign != 0 || (e.nbr >= n && hpts[e.nbr - n] >= nown); };
-        inv_slot.assign((size_t)nslots, -1); inv_hpos.assign((size_t)nhpos, -1);
-        for (int f = 0; f < nf; f++) inv_slot[slot_of[f]] = f;
-        for (int h = 0; h < nh; h++) inv_hpos[hpos_of[h]] = h;
-        fslot_of.assign((size_t)nf, -1); fhpos_of.assign((size_t)nh, -1);
-        int fmd = 0;
+        /* compact numbering of the faces and halo points the contributing entries reference */
+        fface_of.assign((size_t)nf, -1); fhalo_of.assign((size_t)nh, -1);
+        fdeg.assign((size_t)n, 0);
+        int fmd = 0, nff = 0, nfh = 0;
         for (int i = 0; i < n; i++) {
           int c = 0;
-          for (int j = 0; j < deg[i]; j++) {
-            const Ent &e = tile_ents[(size_t)i * md + j];
-            if (!contributes(e)) continue;
-            c++; fslot_of[e.fid] = 0;
-            if (e.nbr >= n) fhpos_of[e.nbr - n] = 0;
-          }
-          fmd = std::max(fmd, c);
+          for (int j = 0; j < deg[i]; j++) c += contributes(tile_ents[(size_t)i * md + j]) ? 1 : 0;
+          fdeg[i] = c; fmd = std::max(fmd, c);
         }
-        int nff = 0, nfh = 0;
-        for (int sl = 0; sl < nslots; sl++) if (inv_slot[sl] >= 0 && fslot_of[inv_slot[sl]] == 0) fslot_of[inv_slot[sl]] = nff++;
-        for (int hp = 0; hp < nhpos; hp++) if (inv_hpos[hp] >= 0 && fhpos_of[inv_hpos[hp]] == 0) fhpos_of[inv_hpos[hp]] = nfh++;
-        std::vector<unsigned char> &fb = ftile_bytes[k];
-        fb.assign(blob_size((uint32_t)nff, (uint32_t)nfh, (uint32_t)fmd, npad), 0);
-        double *fn = (double *)fb.data();
-        uint32_t *fh = (uint32_t *)(fb.data() + blob_halo_off((uint32_t)nff));
-        uint32_t *fe = (uint32_t *)(fb.data() + blob_adj_off((uint32_t)nff, (uint32_t)nfh));
-        for (size_t i = 0; i < (size_t)fmd * npad; i++) fe[i] = CFDP_ADJ_PAD;
-        for (int j = 0; j < (int)(align_up((size_t)nfh * 4, 16) / 4); j++) fh[j] = 0xFFFFFFFFu;
-        for (int f = 0; f < nf; f++)
-          if (fslot_of[f] >= 0) { const int gf = fids[f], sl = fslot_of[f]; fn[3 * sl] = sd->fnormal[gf][0]; fn[3 * sl + 1] = sd->fnormal[gf][1]; fn[3 * sl + 2] = sd->fnormal[gf][2]; }
-        for (int h = 0; h < nh; h++) if (fhpos_of[h] >= 0) fh[fhpos_of[h]] = (uint32_t)out.row_of_point[hpts[h]];
+        ftile_ents.assign((size_t)n * std::max(fmd, 1), Ent{0, 0, 0, -1, -1, -1, 0});
+        fghost.assign((size_t)n * std::max(fmd, 1), 0);
         for (int i = 0; i < n; i++) {
           int c = 0;
           for (int j = 0; j < deg[i]; j++) {
             const Ent &e = tile_ents[(size_t)i * md + j];
             if (!contributes(e)) continue;
-            const uint32_t loc = e.nbr < n ? (uint32_t)e.nbr : (uint32_t)(n_even + fhpos_of[e.nbr - n]);
-            const uint32_t ghost = (e.nbr >= n && hpts[e.nbr - n] >= nown) ? 0x8000u : 0u;
-            fe[(size_t)c * npad + i] = loc | ghost | ((uint32_t)fslot_of[e.fid] << 16) | (e.sign << 31);
+            Ent fe = e;
+            if (fface_of[e.fid] < 0) fface_of[e.fid] = nff++;
+            fe.fid = fface_of[e.fid];
+            if (e.nbr >= n) {
+              if (fhalo_of[e.nbr - n] < 0) fhalo_of[e.nbr - n] = nfh++;
+              fe.nbr = n + fhalo_of[e.nbr - n];
+              fghost[(size_t)i * fmd + c] = hpts[e.nbr - n] >= nown ? 1 : 0;
+            }
+            ftile_ents[(size_t)i * fmd + c] = fe;
             c++;
           }
         }
-        out.ftile_nfaces[k] = nff; out.ftile_nhalo[k] = nfh; out.ftile_maxdeg[k] = fmd;
+        const int nfslots = (int)align_up((size_t)nff, 16), nfhpos = (int)align_up((size_t)nfh, 16);
+        place_all(ftile_ents, fdeg, std::max(fmd, 1), nfh, nff, fhpos_of, nfhpos, fslot_of, nfslots);
+        std::vector<unsigned char> &fb = ftile_bytes[k];
+        fb.assign(blob_size((uint32_t)nfslots, (uint32_t)nfhpos, (uint32_t)fmd, npad), 0);
+        double *fn = (double *)fb.data();
+        uint32_t *fh = (uint32_t *)(fb.data() + blob_halo_off((uint32_t)nfslots));
+        uint32_t *fe = (uint32_t *)(fb.data() + blob_adj_off((uint32_t)nfslots, (uint32_t)nfhpos));
+        for (size_t i = 0; i < (size_t)fmd * npad; i++) fe[i] = CFDP_ADJ_PAD;
+        for (int j = 0; j < nfhpos; j++) fh[j] = 0xFFFFFFFFu;
+        for (int f = 0; f < nf; f++)
+          if (fface_of[f] >= 0) {
+            const int gf = fids[f], sl = fslot_of[fface_of[f]];
+            ASSERT(sl >= 0 && sl < nfslots);
+            fn[3 * sl] = sd->fnormal[gf][0]; fn[3 * sl + 1] = sd->fnormal[gf][1]; fn[3 * sl + 2] = sd->fnormal[gf][2];
+          }
+        for (int h = 0; h < nh; h++)
+          if (fhalo_of[h] >= 0) { ASSERT(fhpos_of[fhalo_of[h]] >= 0 && fhpos_of[fhalo_of[h]] < nfhpos); fh[fhpos_of[fhalo_of[h]]] = (uint32_t)out.row_of_point[hpts[h]]; }
+        for (int i = 0; i < n; i++)
+          for (int c = 0; c < fdeg[i]; c++) {
+            const Ent &e = ftile_ents[(size_t)i * fmd + c];
+            const uint32_t loc = e.nbr < n ? (uint32_t)e.nbr : (uint32_t)(n_even + fhpos_of[e.nbr - n]);
+            fe[(size_t)c * npad + i] = loc | (fghost[(size_t)i * fmd + c] ? 0x8000u : 0u) | ((uint32_t)fslot_of[e.fid] << 16) | (e.sign << 31);
+          }
+        out.ftile_nfaces[k] = nfslots; out.ftile_nhalo[k] = nfhpos; out.ftile_maxdeg[k] = fmd;
       }
 
       /* shared-memory wavefront estimate of the face walk: 7 var words + 3 normal words per face end */

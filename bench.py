@@ -100,7 +100,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the unmodified reference (oracle/_ref) on the host cores
 # ----------------------------------------------------------------------------------------------
-def run_reference_sample(steps, warmup, mpoints=2.0, variant="mpi_async"):
+def run_reference_sample(steps, warmup, mpoints=2.0, variant="mpi_async", with_flux=False):
     """Times the reference's own CPU implementation (oracle/_ref/ref_harness: unmodified
     gradients.c / exchange_data_mpi.c over the shm-MPI shim) on a bounded sample of the workload:
     same mesh family and 8-domain partition, `mpoints` million points.  Falls back to the C
@@ -118,7 +118,7 @@ def run_reference_sample(steps, warmup, mpoints=2.0, variant="mpi_async"):
         faces = int(sum(int(((d["fpoint"][:, 0] < d["nown"]) | (d["fpoint"][:, 1] < d["nown"])).sum()) for d in doms))
         threads = max(1, ncores // 8)
         res = O.run_ref(prefix, 1, 8, variant, steps, os.path.join(tmp, "out"), threads=threads, repeats=max(2, 1 + (1 if warmup else 0)),
-                        timeout=1500)
+                        timeout=1500, with_flux=with_flux)
         best = max(r["time"]["best_s"] for r in res)   # slowest rank of the best repeat
         kind, cores = "reference", min(ncores, 8 * threads)
         sample = (f"{n[0]}x{n[1]}x{n[2]} lattice ({sum(d['nown'] for d in doms)/1e6:.2f} M points, {faces/1e6:.2f} M faces), 8 ranks x "
@@ -318,6 +318,9 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             cpu, _, _ = run_reference_sample(25, 1, mpoints=args.cpu_mpoints, variant=args.variant)
+            if flux is not None and cpu.get("kind") == "reference":   # the reference's whole iteration (solver.c:45-55) on the same sample
+                cf, _, _ = run_reference_sample(25, 1, mpoints=args.cpu_mpoints, variant=args.variant, with_flux=True)
+                flux["cpu_reference_faces_per_s_grad_halo_flux"] = cf["value"]
         except Exception as ex:  # the baseline is reported, never required
             cpu = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="reference", sample=f"failed: {ex}")
 

@@ -1333,6 +1333,25 @@ extern "C" int cfdp_get_row_owner(long long row, int *domain, int *point)
   return -1;
 }
 
+/* raw tile blob for tests (host copy: available between cfdp_plan and cfdp_commit).  which = 0: gradient blob,
+ * 1: pseudo-flux blob.  desc8 = {row0, npts, nhalo, nfaces, maxdeg, npad, blob_bytes, halo_off}; halo rows are device rows. */
+extern "C" long long cfdp_get_tile_blob(const solver_data *sd, int tile, int which, unsigned *desc8, unsigned char *bytes, long long capacity)
+{
+  Engine &E = g_eng;
+  Domain *d = engine_find_domain(sd);
+  if (!d || !E.planned || E.committed) return -1;
+  const DomainSchedule &s = d->sch;
+  if (tile < 0 || tile >= s.ntiles) return -1;
+  if (which == 1 && !E.sopt.flux_blob) return -1;
+  const long long slot = tile < s.nboundary ? d->tile0_b + tile : d->tile0_i + (tile - s.nboundary);
+  const TileDesc &t = which ? E.h_ftiles[(size_t)slot] : E.h_tiles[(size_t)slot];
+  const std::vector<unsigned char> &b = which ? s.fblob : s.blob;
+  const uint64_t off = which ? s.ftile_blob[(size_t)tile] : s.tile_blob[(size_t)tile];
+  if (desc8) { desc8[0] = t.row0; desc8[1] = t.npts; desc8[2] = t.nhalo; desc8[3] = t.nfaces; desc8[4] = t.maxdeg; desc8[5] = t.npad; desc8[6] = t.blob_bytes; desc8[7] = t.halo_off; }
+  if (bytes && capacity >= (long long)t.blob_bytes) memcpy(bytes, &b[(size_t)off], t.blob_bytes);
+  return (long long)t.blob_bytes;
+}
+
 extern "C" int cfdp_get_tile_exports(int tile, int capacity, unsigned *src_row, unsigned *dst, int *kind)
 {
   Engine &E = g_eng;

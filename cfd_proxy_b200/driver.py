@@ -238,6 +238,27 @@ class Session:
         assert n == nfaces
         return f[:nfaces], h[:nhalo]
 
+    def tile_blob(self, d: HostedDomain, t: int, flux: bool = False):
+        """Raw blob of tile t of domain d (host copy, before cfdp_commit): dict with the descriptor fields, normals
+        [nfaces,3], halo device rows [nhalo] and the ELL adjacency [maxdeg, npad] (uint32)."""
+        desc = (C.c_uint * 8)()
+        n = self.lib.cfdp_get_tile_blob(C.byref(d.sd), t, 1 if flux else 0, desc, None, 0)
+        if n < 0:
+            raise RuntimeError("tile blob not available (plan first, before commit)")
+        buf = np.zeros(max(int(n), 1), np.uint8)
+        self.lib.cfdp_get_tile_blob(C.byref(d.sd), t, 1 if flux else 0, desc, buf.ctypes.data_as(C.POINTER(C.c_ubyte)), int(n))
+        row0, npts, nhalo, nfaces, maxdeg, npad, nbytes, halo_off = (int(x) for x in desc)
+        adj_off = halo_off + (nhalo * 4 + 15) // 16 * 16
+        return dict(row0=row0, npts=npts, nhalo=nhalo, nfaces=nfaces, maxdeg=maxdeg, npad=npad, bytes=nbytes,
+                    normals=buf[:nfaces * 24].view(np.float64).reshape(nfaces, 3),
+                    halo_rows=buf[halo_off:halo_off + nhalo * 4].view(np.uint32),
+                    ell=buf[adj_off:adj_off + maxdeg * npad * 4].view(np.uint32).reshape(maxdeg, npad))
+
+    def row_owner(self, row: int):
+        dom, pt = C.c_int(), C.c_int()
+        rc = self.lib.cfdp_get_row_owner(int(row), C.byref(dom), C.byref(pt))
+        return (dom.value, pt.value) if rc == 0 else None
+
     def pack_list(self, d: HostedDomain, k: int) -> np.ndarray:
         out = np.zeros(max(d.cd.sendcount[k], 1), np.int32)
         n = self.lib.cfdp_get_pack_list(C.byref(d.cd), k, out.ctypes.data_as(L.c_int_p))

@@ -124,7 +124,7 @@ EXPORTED = [
     "cfdp_configure", "cfdp_init_communication_domain", "cfdp_nccl_get_unique_id", "cfdp_nccl_init",
     "cfdp_commit", "cfdp_plan", "cfdp_set_int_exchange", "cfdp_get_peer_plan", "cfdp_get_exchange_entry", "cfdp_get_tile_exports", "cfdp_get_row_owner", "cfdp_var_to_device", "cfdp_grad_to_host", "cfdp_set_resident", "cfdp_set_exact",
     "cfdp_iterate", "cfdp_step_e2e", "cfdp_device_synchronize", "cfdp_finalize", "cfdp_get_stats",
-    "cfdp_get_schedule", "cfdp_get_tile", "cfdp_get_pack_list", "cfdp_get_unpack_list", "cfdp_get_sendbuf",
+    "cfdp_get_schedule", "cfdp_get_tile", "cfdp_get_tile_blob", "cfdp_get_pack_list", "cfdp_get_unpack_list", "cfdp_get_sendbuf",
     "cfdp_mesh_num_domains", "cfdp_mesh_count_faces_global", "cfdp_mesh_gen_domain",
     "cfdp_mesh_free_domain", "cfdp_mesh_fill_var", "cfdp_mesh_var_value", "cfdp_attach_mesh",
 ]
@@ -198,6 +198,7 @@ def load() -> C.CDLL:
     sig("cfdp_get_stats", None, P(Stats))
     sig("cfdp_get_schedule", C.c_int, sd_p, P(ScheduleView))
     sig("cfdp_get_tile", C.c_int, sd_p, C.c_int, c_int_p, c_int_p)
+    sig("cfdp_get_tile_blob", C.c_longlong, sd_p, C.c_int, C.c_int, P(C.c_uint), P(C.c_ubyte), C.c_longlong)
     sig("cfdp_get_pack_list", C.c_int, cd_p, C.c_int, c_int_p)
     sig("cfdp_get_unpack_list", C.c_int, cd_p, C.c_int, c_int_p)
     sig("cfdp_get_sendbuf", C.c_int, cd_p, C.c_int, c_dbl_p)

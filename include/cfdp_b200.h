@@ -245,6 +245,11 @@ typedef struct {
 int cfdp_get_schedule(const solver_data *sd, cfdp_schedule_view *v);
 /* raw tile contents for tests: returns counts, fills caller buffers when non-NULL */
 int cfdp_get_tile(const solver_data *sd, int tile, int *face_ids /*[nfaces]*/, int *halo_points /*[nhalo]*/);
+/* raw tile blob (host copy, between cfdp_plan and cfdp_commit): which = 0 gradient blob, 1 pseudo-flux blob;
+ * desc8 = {row0, npts, nhalo, nfaces, maxdeg, npad, blob_bytes, halo_off}; returns blob_bytes or -1.  Layout:
+ * [normals nfaces*3 f64][pad16][halo device rows nhalo u32][pad16][ELL maxdeg*npad u32]; ELL entry = tile-local
+ * point | ghost << 15 | face slot << 16 | (point is p1) << 31, 0xFFFFFFFF = none; local >= CFDP_HALO_BASE(npts) = halo */
+long long cfdp_get_tile_blob(const solver_data *sd, int tile, int which, unsigned *desc8, unsigned char *bytes, long long capacity);
 /* device-side halo lists of a hosted domain in HOST numbering: rows packed for partner k and rows unpacked from k */
 int cfdp_get_pack_list(const comm_data *cd, int partner, int *points /*[sendcount[partner]]*/);
 int cfdp_get_unpack_list(const comm_data *cd, int partner, int *points /*[recvcount[partner]]*/);

@@ -327,7 +327,7 @@ def main():
     if rank == 0:
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-            ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+            ms_per_step=ms / args.steps, iterations_per_s=1e3 * args.steps / ms, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
             data="synthetic",
             config=dict(workload=workload, points=int(n[0] * n[1] * n[2]), faces_per_iteration=int(faces_total),
                         domains=8, domains_per_gpu=8 // world, point_order=args.order, tile_points=int(st.tile_points),
@@ -343,6 +343,9 @@ def main():
                       exchange_ms=max(ms_bulk - ms_kc, 0.0),
                       hidden_frac=(1.0 - max(ms_ovl - ms_kc, 0.0) / (ms_bulk - ms_kc)) if (world > 1 and ms_bulk > ms_kc * 1.005) else None,
                       nvlink_bytes_per_iteration_per_gpu=int(st.send_rows_remote) * 168,
+                      # the un-overlapped exchange (pack is fused into the kernel, so this is transfer + unpack) against NVLink 5: 900 GB/s per direction
+                      nvlink_gbs=(int(st.send_rows_remote) * 168 / ((ms_bulk - ms_kc) * 1e-3) / 1e9) if (world > 1 and ms_bulk > ms_kc) else None,
+                      nvlink_frac_of_900GBps=(int(st.send_rows_remote) * 168 / ((ms_bulk - ms_kc) * 1e-3) / 1e9 / 900.0) if (world > 1 and ms_bulk > ms_kc) else None,
                       note="hidden_frac = 1 - (t_overlapped - t_comm_free) / (t_bulk_sync - t_comm_free); medians of 5 interleaved bursts per variant; variant timed: " + args.variant),
             flux=flux, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line))

@@ -87,6 +87,7 @@ struct ScheduleOptions {
   int bank_placement;  /* 1 = place face slots and halo rows by shared-memory bank (fewer conflicts), 0 = discovery order */
   int slack_slots, slack_halo; /* spare face slots / halo positions per tile for the bank placement */
   int flux_blob;       /* 1 = also build the pseudo-flux blobs */
+  int refine_rounds;   /* local-search sweeps of the bank placement after the greedy pass (0 = greedy only) */
   int sort_in_tile;    /* 1 = points of a tile in ascending file numbering, 0 = in growth (BFS) order */
   int stage_budget;    /* bytes one tile may occupy in shared memory (blob + var rows + volumes); 0 = no limit */
 };

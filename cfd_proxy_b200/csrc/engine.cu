@@ -239,6 +239,7 @@ extern "C" int cfdp_configure(int proc_rank, int nprocs, int ndomains_total, int
   E.sopt.order = env_int("CFDP_TILE_ORDER", 0);
   E.sopt.sort_in_tile = env_int("CFDP_SORT_IN_TILE", 1);
   E.sopt.flux_blob = env_int("CFDP_FLUX_BLOB", 1);
+  E.sopt.refine_rounds = env_int("CFDP_PLACE_REFINE", 0);
   E.sopt.bank_placement = env_int("CFDP_BANK_PLACEMENT", 1);
   E.sopt.slack_slots = env_int("CFDP_SLACK_SLOTS", 0);
   E.sopt.slack_halo = env_int("CFDP_SLACK_HALO", 0);

@@ -225,7 +225,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
       lmap.assign((size_t)nall, -1);
       struct Key { int tt, p1, p0, face, nb; };
       std::vector<Key> keys;
-      std::vector<int> nbr_of, deg, goff, glist, fill, newP;
+      std::vector<int> nbr_of, deg, goff, glist, fill, newP, rcls;
       std::vector<unsigned char> cnt, gmax;
 #pragma omp for schedule(dynamic, 16)
       for (int t = 0; t < ntiles; t++) {
@@ -271,6 +271,69 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
             }
         }
         const int ngrp = ((n + 15) / 16) * md;
+        if (opt.refine_rounds > 0) {
+          /* hill climbing from the file order: two points of a 16-block trade places when that lowers the sum over
+           * groups of the fullest class; never worse than the file order, so the result is always kept */
+          cnt.assign((size_t)ngrp * 16, 0); gmax.assign((size_t)ngrp, 0);
+          rcls.resize((size_t)n);
+          for (int r = 0; r < n; r++) {
+            rcls[r] = r & 15;
+            for (int x = goff[r]; x < goff[(size_t)r + 1]; x++) if (glist[x] >= 0) cnt[(size_t)glist[x] * 16 + (r & 15)]++;
+          }
+          auto remax = [&](int gi) { const unsigned char *cc = &cnt[(size_t)gi * 16]; int mx = 0; for (int x = 0; x < 16; x++) mx = std::max(mx, (int)cc[x]); return mx; };
+          for (int gi = 0; gi < ngrp; gi++) gmax[gi] = (unsigned char)remax(gi);
+          auto shift = [&](int r, int from, int to) {
+            for (int x = goff[r]; x < goff[(size_t)r + 1]; x++) if (glist[x] >= 0) { cnt[(size_t)glist[x] * 16 + from]--; cnt[(size_t)glist[x] * 16 + to]++; }
+          };
+          auto touched_delta = [&](int ra, int rb) { /* objective change over the groups of ra and rb, from the stored gmax */
+            int d = 0;
+            for (int x = goff[ra]; x < goff[(size_t)ra + 1]; x++) if (glist[x] >= 0) d += remax(glist[x]) - gmax[glist[x]];
+            for (int x = goff[rb]; x < goff[(size_t)rb + 1]; x++) {
+              const int gi = glist[x];
+              if (gi < 0) continue;
+              bool both = false;
+              for (int y = goff[ra]; y < goff[(size_t)ra + 1]; y++) if (glist[y] == gi) both = true;
+              if (!both) d += remax(gi) - gmax[gi];
+            }
+            return d;
+          };
+          for (int round = 0; round < opt.refine_rounds; round++) {
+            int improved = 0;
+            for (int b0 = 0; b0 < n; b0 += 16) {
+              const int m = std::min(16, n - b0);
+              for (int ra = b0; ra < b0 + m; ra++) {
+                bool critical = false;
+                for (int x = goff[ra]; x < goff[(size_t)ra + 1] && !critical; x++) {
+                  const int gi = glist[x];
+                  critical = gi >= 0 && gmax[gi] > 1 && cnt[(size_t)gi * 16 + rcls[ra]] == gmax[gi];
+                }
+                if (!critical) continue;
+                int best_d = 0, best_rb = -1;
+                for (int rb = b0; rb < b0 + m; rb++) {
+                  if (rb == ra) continue;
+                  const int ca = rcls[ra], cb = rcls[rb];
+                  shift(ra, ca, cb); shift(rb, cb, ca);
+                  const int d = touched_delta(ra, rb);
+                  shift(ra, cb, ca); shift(rb, ca, cb);
+                  if (d < best_d) { best_d = d; best_rb = rb; }
+                }
+                if (best_rb < 0) continue;
+                const int ca = rcls[ra], cb = rcls[best_rb];
+                shift(ra, ca, cb); shift(best_rb, cb, ca);
+                rcls[ra] = cb; rcls[best_rb] = ca;
+                for (int x = goff[ra]; x < goff[(size_t)ra + 1]; x++) if (glist[x] >= 0) gmax[glist[x]] = (unsigned char)remax(glist[x]);
+                for (int x = goff[best_rb]; x < goff[(size_t)best_rb + 1]; x++) if (glist[x] >= 0) gmax[glist[x]] = (unsigned char)remax(glist[x]);
+                improved++;
+              }
+            }
+            if (!improved) break;
+          }
+          newP.assign((size_t)n, -1);
+          for (int r = 0; r < n; r++) { const int np_ = (r & ~15) + rcls[r]; ASSERT(np_ < n && newP[np_] < 0); newP[np_] = P[r]; }
+          for (int i = 0; i < n; i++) lmap[P[i]] = -1;
+          for (int i = 0; i < n; i++) P[i] = newP[i];
+          continue;
+        }
         cnt.assign((size_t)ngrp * 16, 0); gmax.assign((size_t)ngrp, 0);
         newP.assign((size_t)n, -1);
         for (int b0 = 0; b0 < n; b0 += 16) {
@@ -426,6 +489,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
     std::vector<int> deg, slot_of, hpos_of;      /* fid -> slot, halo k -> position */
     std::vector<unsigned char> cntv, cntn;       /* [group][16] */
     std::vector<int> grp_off, grp_list;          /* per face / per halo point: distinct groups */
+    std::vector<int> cls; std::vector<std::vector<int>> members; /* class of an object; objects of a class */
     std::vector<Ent> ftile_ents; std::vector<int> fdeg, fface_of, fhalo_of, fslot_of, fhpos_of; std::vector<unsigned char> fghost; /* pseudo-flux blob */
 #pragma omp for schedule(dynamic, 16)
     for (int k = 0; k < ntiles; k++) {
@@ -538,6 +602,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
           }
           const int cap = npos / 16;
           int used[16] = {0};
+          cls.assign((size_t)nobj, -1);
           for (int o = 0; o < nobj; o++) {
             int best = -1, best_cost = 1 << 30;
             for (int c0 = 0; c0 < 16; c0++) {
@@ -557,10 +622,79 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
             }
             ASSERT(best >= 0);
             for (int t = grp_off[o]; t < grp_off[(size_t)o + 1]; t++) if (grp_list[t] >= 0) cnt[(size_t)grp_list[t] * 16 + best]++;
-            /* position with (base_mod + pos) mod 16 == best */
-            const int first = ((best - base_mod) % 16 + 16) % 16;
-            pos_of[o] = first + 16 * used[best];
+            cls[o] = best;
             used[best]++;
+          }
+          /* refinement: an object that alone holds a group at its maximum moves to a class where it does not, into a
+           * free position or by trading places with an object for which the trade costs nothing.  The objective is the
+           * estimator's: the sum over groups of the fullest class. */
+          auto gmax = [&](int gi) { const unsigned char *cc = &cnt[(size_t)gi * 16]; int mx = 0; for (int x = 0; x < 16; x++) mx = std::max(mx, (int)cc[x]); return mx; };
+          auto n_at = [&](int gi, int v) { const unsigned char *cc = &cnt[(size_t)gi * 16]; int k = 0; for (int x = 0; x < 16; x++) k += cc[x] == v; return k; };
+          auto move_delta = [&](int o, int from, int to) { /* change of the objective when o goes from class `from` to `to` (counts include o in `from`) */
+            int d = 0;
+            for (int t = grp_off[o]; t < grp_off[(size_t)o + 1]; t++) {
+              const int gi = grp_list[t];
+              if (gi < 0) continue;
+              const unsigned char *cc = &cnt[(size_t)gi * 16];
+              const int mx = gmax(gi);
+              const int mx_wo = (cc[from] == mx && n_at(gi, mx) == 1) ? mx - 1 : mx; /* maximum without o */
+              d += std::max(mx_wo, cc[to] + 1) - mx;
+            }
+            return d;
+          };
+          auto apply_move = [&](int o, int from, int to) {
+            for (int t = grp_off[o]; t < grp_off[(size_t)o + 1]; t++) {
+              const int gi = grp_list[t];
+              if (gi < 0) continue;
+              cnt[(size_t)gi * 16 + from]--; cnt[(size_t)gi * 16 + to]++;
+            }
+            cls[o] = to;
+          };
+          for (int round = 0; round < opt.refine_rounds; round++) {
+            members.assign(16, std::vector<int>());
+            for (int o = 0; o < nobj; o++) members[(size_t)cls[o]].push_back(o);
+            int improved = 0;
+            for (int o = 0; o < nobj; o++) {
+              const int c = cls[o];
+              bool critical = false;
+              for (int t = grp_off[o]; t < grp_off[(size_t)o + 1] && !critical; t++) {
+                const int gi = grp_list[t];
+                if (gi < 0) continue;
+                const int mx = gmax(gi);
+                critical = mx > 1 && cnt[(size_t)gi * 16 + c] == mx && n_at(gi, mx) == 1;
+              }
+              if (!critical) continue;
+              int best_d = 0, best_c = -1, best_partner = -1;
+              for (int c2 = 0; c2 < 16; c2++) {
+                if (c2 == c) continue;
+                const int d1 = move_delta(o, c, c2);
+                if (d1 >= 0) continue;
+                if (used[c2] < cap) { if (d1 < best_d) { best_d = d1; best_c = c2; best_partner = -1; } continue; }
+                /* trade: apply o's move, then look for a partner in c2 whose move to c keeps the total below zero */
+                apply_move(o, c, c2);
+                int tries = 0;
+                for (int q : members[(size_t)c2]) {
+                  if (cls[q] != c2 || q == o) continue;
+                  if (++tries > 24) break;
+                  const int d2 = move_delta(q, c2, c);
+                  if (d1 + d2 < best_d) { best_d = d1 + d2; best_c = c2; best_partner = q; }
+                }
+                apply_move(o, c2, c);
+              }
+              if (best_c < 0) continue;
+              apply_move(o, c, best_c);
+              if (best_partner >= 0) { apply_move(best_partner, best_c, c); members[(size_t)c].push_back(best_partner); }
+              else { used[c]--; used[best_c]++; }
+              members[(size_t)best_c].push_back(o);
+              improved++;
+            }
+            if (!improved) break;
+          }
+          int fillc[16] = {0};
+          for (int o = 0; o < nobj; o++) {
+            /* position with (base_mod + pos) mod 16 == class */
+            const int first = ((cls[o] - base_mod) % 16 + 16) % 16;
+            pos_of[o] = first + 16 * fillc[cls[o]]++;
           }
         };
         place(nH, false, cntv, HP, NHP, n_even & 15);

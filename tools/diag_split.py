@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Diagnostic for the experimental split-roles kernel path: which rows come out wrong (tile, position, chunk slot)?"""
+"""Diagnostic that located the split-roles bug (a stray 8-byte cp.async of the non-gathering lanes, profiles/README.md):
+which rows come out wrong (tile, position in the tile, slot in the chunk), how many of their 21 columns, and whether a constant
+var hides the damage (DIAG_CONST_VAR=1).  Kept as a template for localising parity damage; prints zeros on a healthy build."""
 import os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

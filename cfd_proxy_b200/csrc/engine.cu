@@ -472,8 +472,16 @@ extern "C" void cfdp_plan(void)
 
   /* 1. face schedules: domains in parallel when several are hosted */
   if (nh > 1) {
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int i = 0; i < nh; i++) build_schedule(E.doms[i]->sd, E.doms[i]->cd, E.sopt, E.doms[i]->sch);
+    /* domains side by side, and the cores that are left over inside each domain's builder (nested regions) */
+    const int ncores = omp_get_max_threads(), outer = std::min(nh, ncores), inner = std::max(1, ncores / outer);
+    const int levels = omp_get_max_active_levels();
+    if (inner > 1) omp_set_max_active_levels(std::max(levels, 2));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(outer)
+    for (int i = 0; i < nh; i++) {
+      omp_set_num_threads(inner); /* this thread's nested regions */
+      build_schedule(E.doms[i]->sd, E.doms[i]->cd, E.sopt, E.doms[i]->sch);
+    }
+    omp_set_max_active_levels(levels);
   } else {
     build_schedule(E.doms[0]->sd, E.doms[0]->cd, E.sopt, E.doms[0]->sch);
   }

@@ -3,7 +3,7 @@
 which rows come out wrong (tile, position in the tile, slot in the chunk), how many of their 21 columns, and whether a constant
 var hides the damage (DIAG_CONST_VAR=1).  Kept as a template for localising parity damage; prints zeros on a healthy build."""
 import os, sys, collections
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # test infrastructure: uses the oracle as the checker
 import numpy as np
 import cfd_proxy_b200.mesh as M
 from cfd_proxy_b200.driver import Session

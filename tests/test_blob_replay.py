@@ -76,6 +76,19 @@ def test_gradient_blob_replay_bit_identical(session_factory, n, p, order, hexfra
             assert (b["ell"][:, npts:] == PAD).all()                       # padding lanes hold no entries
 
 
+def test_replay_with_refined_placement(session_factory, monkeypatch):
+    """CFDP_PLACE_REFINE (hill climbing on top of the greedy bank placement) permutes rows, slots and halo positions:
+    the results must not change, the estimated wavefronts must not grow."""
+    n, p, order, hexfrac, tile, torder = CASES[0]
+    S, doms, recv, send = replay_setup(session_factory, n, p, order, hexfrac, tile, torder)
+    base = S.stats().lds_wavefronts_est
+    monkeypatch.setenv("CFDP_PLACE_REFINE", "3")
+    test_gradient_blob_replay_bit_identical(session_factory, n, p, order, hexfrac, tile, torder)
+    test_flux_blob_replay_bit_identical(session_factory, n, p, order, hexfrac, tile, torder)
+    S2, _, _, _ = replay_setup(session_factory, n, p, order, hexfrac, tile, torder)
+    assert S2.stats().lds_wavefronts_est <= base
+
+
 @pytest.mark.parametrize("n,p,order,hexfrac,tile,torder", CASES)
 def test_flux_blob_replay_bit_identical(session_factory, n, p, order, hexfrac, tile, torder):
     S, doms, recv, send = replay_setup(session_factory, n, p, order, hexfrac, tile, torder)

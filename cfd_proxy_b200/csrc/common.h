@@ -30,12 +30,19 @@ struct TileDesc {
   uint32_t row0;       /* first device row of the tile's points (global over the GPU) */
   uint16_t npts;       /* own points in the tile */
   uint16_t nhalo;      /* points outside the tile its faces reference */
-  uint32_t nfaces;     /* face records in the tile blob */
+  uint16_t nfaces;     /* face slots in the tile blob (multiple of 16, <= 32767) */
+  uint16_t zslot;      /* a face slot no face uses: its normal is (0,0,0).  The production kernel turns padding entries of the
+                        * adjacency into (neighbour = the point itself, face = zslot): a contribution of exactly +-0 */
   uint16_t maxdeg;     /* ELL depth: max incident faces of a tile point */
   uint16_t npad;       /* ELL row pitch (npts rounded up to 32) */
-  uint64_t blob;       /* byte offset of the tile blob (128-byte aligned) */
+  uint32_t blob128;    /* offset of the tile blob in units of 128 bytes */
+  uint32_t hrow0;      /* first row of the tile's block in the packed halo array (nhalo rows, see engine.cu) */
   uint32_t blob_bytes; /* size of the tile blob (multiple of 128) */
   uint32_t halo_off;   /* byte offset of the halo row list inside the blob (normals come first) */
+#ifdef __CUDACC__
+  __host__ __device__
+#endif
+  size_t blob_off() const { return (size_t)blob128 * 128; }
 };
 /* tile-local point index: [0,npts) own points of the tile, halo points from CFDP_HALO_BASE(npts) on
  * (even, so that the own var rows can be fetched as one 16-byte granular bulk copy) */
@@ -62,6 +69,7 @@ struct DomainSchedule {
   std::vector<int> tile_row0;           /* [ntiles+1] */
   std::vector<int> tile_npts, tile_nfaces, tile_nhalo, tile_maxdeg, tile_is_boundary;
   std::vector<int> tile_nslots, tile_nhpos; /* shared-memory positions of face normals / halo rows (multiples of 16, >= the counts) */
+  std::vector<int> tile_zslot;          /* per tile: an unused face slot (zero normal), see TileDesc::zslot */
   std::vector<uint64_t> tile_blob;      /* [ntiles+1] byte offsets into blob */
   std::vector<unsigned char> blob;      /* halo rows domain-relative until commit rebases them */
   std::vector<int> tile_face_ids;       /* concatenated original face ids in slot order */

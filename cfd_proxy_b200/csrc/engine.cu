@@ -31,6 +31,7 @@
 #include <omp.h>
 #include "common.h"
 #include "gg_kernels.cuh"
+#include "gg_kernels_v4.cuh"
 #include "flux_kernels.cuh"
 
 #define CUDA_CHECK(call)                                                                           \
@@ -112,13 +113,14 @@ struct Engine {
   /* device */
   long long rows = 0, ntiles = 0, nbtiles = 0;
   double *d_var = nullptr, *d_grad = nullptr, *d_pvol = nullptr;
+  double *d_hhalo = nullptr; long long halo_rows = 0; /* packed halo rows: per tile a contiguous copy of the half-var rows of its halo positions (gg_kernels.cuh) */
   unsigned char *d_fblob = nullptr; TileDesc *d_ftiles = nullptr; std::vector<TileDesc> h_ftiles; std::vector<size_t> fblob_base; size_t fblob_bytes = 0; /* pseudo-flux blobs (same tile order as h_tiles) */
   double *d_flux = nullptr; int with_flux = 0; uint32_t flux_smem = 0; double last_flux_ms = 0; long long flux_alg_bytes = 0; /* pseudo flux (flux.c), lazily allocated */
   unsigned char *d_blob = nullptr;
   TileDesc *d_tiles = nullptr;
   size_t blob_bytes = 0;
   int smem_bytes = 0, region0_doubles = 0, block_threads = 0;
-  int kernel_version = 2, chunk = 16, smem_v1 = 0; ggk::PipeLayout pipe = {0, 256, nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr};
+  int kernel_version = 2, chunk = 16, smem_v1 = 0, persistent = 0; ggk::PipeLayout pipe = {}; ggk4::PipeLayout pipe4 = {}; uint32_t max_hvpv = 0;
   unsigned long long *d_progress = nullptr; unsigned long long progress_target = 0; int fused_signal = 1;
   /* fused pack: per boundary tile, the rows other domains need (export lists), written by the gradient kernel itself */
   std::vector<uint32_t> h_exp_off, h_exp_src, h_exp_dst; uint32_t *d_exp_off = nullptr, *d_exp_src = nullptr, *d_exp_dst = nullptr; int fused_pack = 1;
@@ -387,20 +389,53 @@ static void launch_rows_copy(double *dst, const uint32_t *dst_rows, const double
   g_eng.launches++;
 }
 
+/* refresh the packed halo rows of tiles [tile0, tile0 + ntiles) from the device var rows (after every upload of var) */
+static void launch_halo_pack(long long tile0, long long ntiles, cudaStream_t st)
+{
+  Engine &E = g_eng;
+  if (ntiles <= 0) return;
+  const unsigned grid = (unsigned)std::min<long long>(ntiles, 148 * 16);
+  ggk::halo_pack_kernel<<<grid, 256, 0, st>>>(E.d_tiles + tile0, (int)ntiles, E.d_blob, E.d_var, E.d_hhalo);
+  CUDA_CHECK(cudaGetLastError());
+  E.launches++;
+}
+static void launch_halo_pack_domain(const Domain *d, cudaStream_t st)
+{
+  launch_halo_pack(d->tile0_b, d->sch.nboundary, st);
+  launch_halo_pack(d->tile0_i, d->sch.ntiles - d->sch.nboundary, st);
+}
+
 static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st, int nsignal = 0, bool exports = false)
 {
   Engine &E = g_eng;
   if (ntiles <= 0) return;
-  E.pipe.nsignal = nsignal; E.pipe.progress = E.d_progress;
-  E.pipe.tile_base = (int)tile0;
-  E.pipe.nexport = (exports && E.fused_pack && E.kernel_version == 2) ? (int)E.nbtiles : 0;
-  E.pipe.exp_off = E.d_exp_off; E.pipe.exp_src = E.d_exp_src; E.pipe.exp_dst = E.d_exp_dst; E.pipe.sendbuf = E.d_sendbuf;
   if (E.kernel_version == 2) {
-    const unsigned grid = (unsigned)((ntiles + E.chunk - 1) / E.chunk);
+    ggk::PipeLayout &P = E.pipe;
+    P.nsignal = nsignal; P.progress = E.d_progress;
+    P.tile_base = (int)tile0;
+    P.nexport = (exports && E.fused_pack) ? (int)E.nbtiles : 0;
+    P.exp_off = E.d_exp_off; P.exp_src = E.d_exp_src; P.exp_dst = E.d_exp_dst;
+    P.exp_base[0] = E.d_grad; P.exp_base[1] = E.d_sendbuf;
+    unsigned grid;
+    if (E.persistent > 0) { /* interleaved: CTA b walks tiles b, b + grid, ...: the tiles in flight at any time are neighbours in the tile order */
+      grid = (unsigned)std::min<long long>(ntiles, (long long)E.persistent);
+      P.cstride = 1; P.istride = (int)grid; P.maxcount = 0x7FFFFFFF;
+    } else {
+      grid = (unsigned)((ntiles + E.chunk - 1) / E.chunk);
+      P.cstride = E.chunk; P.istride = 1; P.maxcount = E.chunk;
+    }
     if (E.exact)
-      ggk::gg_tile_pipe_kernel<true><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.chunk, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.pipe);
+      ggk::gg_tile_pipe_kernel<true><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.d_blob, E.d_var, E.d_hhalo, E.d_pvol, E.d_grad, P);
     else
-      ggk::gg_tile_pipe_kernel<false><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.chunk, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.pipe);
+      ggk::gg_tile_pipe_kernel<false><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.d_blob, E.d_var, E.d_hhalo, E.d_pvol, E.d_grad, P);
+  } else if (E.kernel_version == 3) { /* round-1 production kernel, kept for side-by-side timing (no fused pack) */
+    E.pipe4.nsignal = nsignal; E.pipe4.progress = E.d_progress; E.pipe4.tile_base = (int)tile0; E.pipe4.nexport = 0; E.pipe4.exp_off = E.d_exp_off; E.pipe4.exp_src = E.d_exp_src; E.pipe4.exp_dst = E.d_exp_dst; E.pipe4.sendbuf = E.d_sendbuf;
+    const int chunk = std::min(E.chunk, CFDP_MAX_CHUNK_V4);
+    const unsigned grid = (unsigned)((ntiles + chunk - 1) / chunk);
+    if (E.exact)
+      ggk4::gg_tile_pipe_kernel<true><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, chunk, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.pipe4);
+    else
+      ggk4::gg_tile_pipe_kernel<false><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, chunk, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.pipe4);
   } else {
     if (E.exact)
       ggk::gg_tile_kernel<true><<<(unsigned)ntiles, E.block_threads, E.smem_v1, st>>>(E.d_tiles + tile0, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.region0_doubles);
@@ -518,8 +553,9 @@ extern "C" void cfdp_plan(void)
       TileDesc t;
       t.row0 = (uint32_t)(d->rowbase + s.tile_row0[k]);
       t.npts = (uint16_t)s.tile_npts[k]; t.nhalo = (uint16_t)s.tile_nhpos[k];     /* positions, gaps hold 0xFFFFFFFF */
-      t.nfaces = (uint32_t)s.tile_nslots[k]; t.maxdeg = (uint16_t)s.tile_maxdeg[k];
-      t.blob = (uint64_t)(E.blob_base[i] + s.tile_blob[k]);
+      t.nfaces = (uint16_t)s.tile_nslots[k]; t.zslot = (uint16_t)s.tile_zslot[k]; t.maxdeg = (uint16_t)s.tile_maxdeg[k];
+      ASSERT((E.blob_base[i] + s.tile_blob[k]) % 128 == 0);
+      t.blob128 = (uint32_t)((E.blob_base[i] + s.tile_blob[k]) / 128); t.hrow0 = 0; /* assigned below, in launch order */
       t.blob_bytes = (uint32_t)(s.tile_blob[(size_t)k + 1] - s.tile_blob[k]);
       t.npad = (uint16_t)align_up((size_t)s.tile_npts[k], 32);
       t.halo_off = (uint32_t)blob_halo_off(t.nfaces);
@@ -527,12 +563,14 @@ extern "C" void cfdp_plan(void)
       uint32_t *hr = (uint32_t *)(&s.blob[s.tile_blob[k]] + t.halo_off);
       for (int j = 0; j < s.tile_nhpos[k]; j++) if (hr[j] != 0xFFFFFFFFu) hr[j] += (uint32_t)d->rowbase;
       E.max_footprint = std::max(E.max_footprint, ggk::tile_footprint(t.blob_bytes, t.npts, t.nhalo));
+      E.max_hvpv = std::max(E.max_hvpv, ggk::stage_hvar_bytes(t.npts, t.nhalo) + ggk::stage_pvol_bytes(t.npts));
       const size_t slot = (size_t)(k < s.nboundary ? tb++ : ti++);
       E.h_tiles[slot] = t;
       if (fb) { /* the tile's pseudo-flux blob: same format, fewer faces / halo rows / adjacency rows */
         TileDesc f = t;
-        f.nhalo = (uint16_t)s.ftile_nhalo[k]; f.nfaces = (uint32_t)s.ftile_nfaces[k]; f.maxdeg = (uint16_t)s.ftile_maxdeg[k];
-        f.blob = (uint64_t)(E.fblob_base[i] + s.ftile_blob[k]);
+        f.nhalo = (uint16_t)s.ftile_nhalo[k]; f.nfaces = (uint16_t)s.ftile_nfaces[k]; f.zslot = 0; f.maxdeg = (uint16_t)s.ftile_maxdeg[k];
+        ASSERT((E.fblob_base[i] + s.ftile_blob[k]) % 128 == 0);
+        f.blob128 = (uint32_t)((E.fblob_base[i] + s.ftile_blob[k]) / 128); f.hrow0 = 0;
         f.blob_bytes = (uint32_t)(s.ftile_blob[(size_t)k + 1] - s.ftile_blob[k]);
         f.halo_off = (uint32_t)blob_halo_off(f.nfaces);
         uint32_t *fh = (uint32_t *)(&s.fblob[s.ftile_blob[k]] + f.halo_off);
@@ -547,6 +585,8 @@ extern "C" void cfdp_plan(void)
     for (int p = 0; p < s.nall; p++) E.point_of_row[i][(size_t)s.row_of_point[p]] = p;
   }
   ASSERT(tb == E.nbtiles && ti == E.ntiles);
+  E.halo_rows = 0;
+  for (long long t = 0; t < E.ntiles; t++) { ASSERT(E.halo_rows < 0xFFFFFFF0LL); E.h_tiles[(size_t)t].hrow0 = (uint32_t)E.halo_rows; E.halo_rows += E.h_tiles[(size_t)t].nhalo; }
 
   /* 3. exchange plan (thread_comm.c:27-432 / threads.c:571-726 flattened into device row lists) */
   struct Seg { int src, dst; const std::vector<uint32_t> *rows; };
@@ -614,8 +654,9 @@ extern "C" void cfdp_plan(void)
     const size_t nexp = E.h_loc_src.size() + E.h_send_rows.size();
     std::vector<int> etile(nexp); std::vector<uint32_t> esrc(nexp), edst(nexp);
     size_t n = 0;
-    for (size_t i = 0; i < E.h_loc_src.size(); i++, n++) { etile[n] = tile_of(E.h_loc_src[i]); esrc[n] = E.h_loc_src[i]; edst[n] = E.h_loc_dst[i]; }
-    for (size_t i = 0; i < E.h_send_rows.size(); i++, n++) { etile[n] = tile_of(E.h_send_rows[i]); esrc[n] = E.h_send_rows[i]; edst[n] = (uint32_t)i | 0x80000000u; }
+    std::vector<unsigned char> ekind(nexp);
+    for (size_t i = 0; i < E.h_loc_src.size(); i++, n++) { etile[n] = tile_of(E.h_loc_src[i]); esrc[n] = E.h_loc_src[i]; edst[n] = E.h_loc_dst[i]; ekind[n] = 0; }
+    for (size_t i = 0; i < E.h_send_rows.size(); i++, n++) { etile[n] = tile_of(E.h_send_rows[i]); esrc[n] = E.h_send_rows[i]; edst[n] = (uint32_t)i; ekind[n] = 1; }
     E.h_exp_off.assign((size_t)E.nbtiles + 1, 0);
     for (size_t i = 0; i < nexp; i++) { ASSERT(etile[i] < E.nbtiles); E.h_exp_off[(size_t)etile[i] + 1]++; } /* send points live in boundary tiles */
     for (long long t = 0; t < E.nbtiles; t++) E.h_exp_off[(size_t)t + 1] += E.h_exp_off[(size_t)t];
@@ -623,11 +664,54 @@ extern "C" void cfdp_plan(void)
     std::vector<uint32_t> cur(E.h_exp_off.begin(), E.h_exp_off.end() - 1);
     for (size_t i = 0; i < nexp; i++) {
       const uint32_t pos = cur[(size_t)etile[i]]++;
-      E.h_exp_src[pos] = esrc[i] - E.h_tiles[(size_t)etile[i]].row0;   /* tile-local point */
+      E.h_exp_src[pos] = (esrc[i] - E.h_tiles[(size_t)etile[i]].row0) | ((uint32_t)ekind[i] << 16);   /* tile-local point | destination array << 16 */
       E.h_exp_dst[pos] = edst[i];
     }
   }
   E.planned = true;
+}
+
+/* which gradient kernel runs and how its grid walks the tiles.  version 2 = production (gg_tile_pipe_kernel), 3 = the
+ * round-1 kernel (side-by-side timing), 1 = one tile per CTA (second, independent implementation for cross-checks);
+ * chunk = consecutive tiles per CTA; persistent > 0 = that many CTAs walk all tiles, interleaved */
+static void configure_kernel(int version, int chunk, int persistent)
+{
+  Engine &E = g_eng;
+  /* pipelined kernels: one stage [blob | var rows | volumes] per CTA, two CTAs per SM.  The production kernel keeps the
+   * var rows at the END of the stage: they must never overlap the rows the previous tile is still storing (8 zones) */
+  E.pipe.stage_bytes = std::max(E.max_footprint, (uint32_t)(8 * CFDP_ZONE_BYTES) + E.max_hvpv);
+  E.pipe4.stage_bytes = E.max_footprint;
+  E.kernel_version = version;
+  E.chunk = std::max(1, chunk);
+  E.persistent = std::max(0, persistent);
+  E.pipe4.block_points = E.block_threads;
+  E.pipe4.split_roles = env_int("CFDP_SPLIT_ROLES", 1);
+  const int smem_limit = 227 * 1024 - 256;
+  if ((E.kernel_version == 2 || E.kernel_version == 3) && (int)E.pipe.stage_bytes > smem_limit) {
+    fprintf(stderr, "cfdp: pipelined kernel needs %u B of shared memory per stage, falling back to the one-tile-per-CTA kernel "
+                    "(lower CFDP_TILE_POINTS to avoid this)\n", E.pipe.stage_bytes);
+    E.kernel_version = 1;
+  }
+  ASSERT(E.smem_v1 <= smem_limit);
+  E.smem_bytes = E.kernel_version == 2 ? (int)E.pipe.stage_bytes : (E.kernel_version == 3 ? (int)E.pipe4.stage_bytes : E.smem_v1);
+  CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
+  CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
+  if (E.kernel_version == 2) {
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+  } else if (E.kernel_version == 3) {
+    CUDA_CHECK(cudaFuncSetAttribute(ggk4::gg_tile_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ggk4::gg_tile_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+  }
+}
+
+extern "C" int cfdp_set_kernel(int version, int chunk, int persistent)
+{
+  Engine &E = g_eng;
+  if (!E.committed || version < 1 || version > 3) return -1;
+  cfdp_device_synchronize();
+  configure_kernel(version, chunk, persistent);
+  return E.kernel_version;
 }
 
 static void ipc_setup(void);
@@ -660,6 +744,7 @@ extern "C" void cfdp_commit(void)
   CUDA_CHECK(cudaMalloc(&E.d_var, (size_t)E.rows * NGRAD * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&E.d_grad, (size_t)E.rows * CFDP_DIM2 * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&E.d_pvol, (size_t)E.rows * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&E.d_hhalo, (size_t)std::max<long long>(E.halo_rows, 2) * NGRAD * sizeof(double)));
   CUDA_CHECK(cudaMemset(E.d_var, 0, (size_t)E.rows * NGRAD * sizeof(double)));
   CUDA_CHECK(cudaMemset(E.d_grad, 0, (size_t)E.rows * CFDP_DIM2 * sizeof(double)));
   E.stage_bytes = E.max_stage;
@@ -682,29 +767,10 @@ extern "C" void cfdp_commit(void)
   /* v1 (one tile per CTA) */
   E.region0_doubles = (int)align_up((size_t)std::max(E.max_nfaces * 3, E.max_npts * CFDP_DIM2), 2);
   E.smem_v1 = (int)((size_t)E.region0_doubles * 8 + align_up((size_t)E.max_nloc * NGRAD * 8, 16));
-  /* v2 (pipelined): two stages of [blob | var rows | volumes] */
-  E.pipe.stage_bytes = E.max_footprint;
-  E.kernel_version = env_int("CFDP_KERNEL", 2);
-  E.chunk = std::min(CFDP_MAX_CHUNK, std::max(1, env_int("CFDP_CHUNK", 8)));
-  E.pipe.block_points = E.block_threads;
-  E.fused_signal = env_int("CFDP_FUSED_SIGNAL", 1);
-  E.pipe.split_roles = env_int("CFDP_SPLIT_ROLES", 1);
   CUDA_CHECK(cudaMalloc(&E.d_progress, 64)); CUDA_CHECK(cudaMemset(E.d_progress, 0, 64)); E.progress_target = 0;
-  if (env_int("CFDP_PHASE_PROF", 0)) { CUDA_CHECK(cudaMalloc(&E.pipe.prof, 8 * sizeof(unsigned long long))); CUDA_CHECK(cudaMemset(E.pipe.prof, 0, 8 * sizeof(unsigned long long))); }
-  const int smem_limit = 227 * 1024 - 256;
-  if (E.kernel_version == 2 && (int)E.pipe.stage_bytes > smem_limit) {
-    fprintf(stderr, "cfdp: pipelined kernel needs %u B of shared memory per stage, falling back to the one-tile-per-CTA kernel "
-                    "(lower CFDP_TILE_POINTS to avoid this)\n", E.pipe.stage_bytes);
-    E.kernel_version = 1;
-  }
-  ASSERT(E.smem_v1 <= smem_limit);
-  E.smem_bytes = E.kernel_version == 2 ? (int)E.pipe.stage_bytes : E.smem_v1;
-  CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
-  CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
-  if (E.kernel_version == 2) {
-    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
-    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
-  }
+  if (env_int("CFDP_PHASE_PROF", 0)) { CUDA_CHECK(cudaMalloc(&E.pipe.prof, 8 * sizeof(unsigned long long))); CUDA_CHECK(cudaMemset(E.pipe.prof, 0, 8 * sizeof(unsigned long long))); E.pipe4.prof = E.pipe.prof; }
+  E.fused_signal = env_int("CFDP_FUSED_SIGNAL", 1);
+  configure_kernel(env_int("CFDP_KERNEL", 2), env_int("CFDP_CHUNK", 8), env_int("CFDP_PERSISTENT", 0));
 
   E.d_loc_dst = upload(E.h_loc_dst); E.d_loc_src = upload(E.h_loc_src);
   E.d_exp_off = upload(E.h_exp_off); E.d_exp_src = upload(E.h_exp_src); E.d_exp_dst = upload(E.h_exp_dst);
@@ -737,6 +803,7 @@ extern "C" void cfdp_var_to_device(solver_data *sd)
   CUDA_CHECK(cudaMemcpyAsync(E.d_stage, &sd->var[0][0], n * NGRAD * sizeof(double), cudaMemcpyHostToDevice, E.s_comp));
   /* the device keeps hvar = 0.5*var in tile order (exact: power-of-two scaling), see gg_kernels.cuh */
   launch_rows_copy(E.d_var, (const uint32_t *)E.d_rowmap[i], E.d_stage, nullptr, (long long)n, NGRAD, E.s_comp, 0.5);
+  launch_halo_pack_domain(d, E.s_comp);
 }
 
 extern "C" void cfdp_grad_to_host(solver_data *sd)
@@ -1101,6 +1168,7 @@ static void enqueue_step_e2e(int variant)
     /* compute: permute into device rows (halved), this domain's boundary and interior tiles */
     CUDA_CHECK(cudaStreamWaitEvent(E.s_comp, R.ev_up[b], 0));
     launch_rows_copy(E.d_var, (const uint32_t *)E.d_rowmap[(size_t)i], R.var_stage[b], nullptr, (long long)nall, NGRAD, E.s_comp, 0.5);
+    launch_halo_pack_domain(d, E.s_comp);
     CUDA_CHECK(cudaEventRecord(R.ev_var_free[b], E.s_comp));
     launch_gradient(d->tile0_b, d->sch.nboundary, E.s_comp, 0, exchange);
     launch_gradient(d->tile0_i, d->sch.ntiles - d->sch.nboundary, E.s_comp);
@@ -1343,7 +1411,7 @@ extern "C" int cfdp_get_row_owner(long long row, int *domain, int *point)
 }
 
 /* raw tile blob for tests (host copy: available between cfdp_plan and cfdp_commit).  which = 0: gradient blob,
- * 1: pseudo-flux blob.  desc8 = {row0, npts, nhalo, nfaces, maxdeg, npad, blob_bytes, halo_off}; halo rows are device rows. */
+ * 1: pseudo-flux blob.  desc8 = {row0, npts, nhalo, nfaces | zslot << 16, maxdeg, npad, blob_bytes, halo_off}; halo rows are device rows. */
 extern "C" long long cfdp_get_tile_blob(const solver_data *sd, int tile, int which, unsigned *desc8, unsigned char *bytes, long long capacity)
 {
   Engine &E = g_eng;
@@ -1356,7 +1424,7 @@ extern "C" long long cfdp_get_tile_blob(const solver_data *sd, int tile, int whi
   const TileDesc &t = which ? E.h_ftiles[(size_t)slot] : E.h_tiles[(size_t)slot];
   const std::vector<unsigned char> &b = which ? s.fblob : s.blob;
   const uint64_t off = which ? s.ftile_blob[(size_t)tile] : s.tile_blob[(size_t)tile];
-  if (desc8) { desc8[0] = t.row0; desc8[1] = t.npts; desc8[2] = t.nhalo; desc8[3] = t.nfaces; desc8[4] = t.maxdeg; desc8[5] = t.npad; desc8[6] = t.blob_bytes; desc8[7] = t.halo_off; }
+  if (desc8) { desc8[0] = t.row0; desc8[1] = t.npts; desc8[2] = t.nhalo; desc8[3] = (unsigned)t.nfaces | ((unsigned)t.zslot << 16); desc8[4] = t.maxdeg; desc8[5] = t.npad; desc8[6] = t.blob_bytes; desc8[7] = t.halo_off; }
   if (bytes && capacity >= (long long)t.blob_bytes) memcpy(bytes, &b[(size_t)off], t.blob_bytes);
   return (long long)t.blob_bytes;
 }
@@ -1367,9 +1435,9 @@ extern "C" int cfdp_get_tile_exports(int tile, int capacity, unsigned *src_row, 
   if (!E.planned || tile < 0 || tile >= E.nbtiles) return -1;
   const uint32_t e0 = E.h_exp_off[(size_t)tile], e1 = E.h_exp_off[(size_t)tile + 1];
   for (uint32_t e = e0; e < e1 && (int)(e - e0) < capacity; e++) {
-    if (src_row) src_row[e - e0] = E.h_tiles[(size_t)tile].row0 + E.h_exp_src[e];
-    if (dst) dst[e - e0] = E.h_exp_dst[e] & 0x7FFFFFFFu;
-    if (kind) kind[e - e0] = (E.h_exp_dst[e] >> 31) & 1;
+    if (src_row) src_row[e - e0] = E.h_tiles[(size_t)tile].row0 + (E.h_exp_src[e] & 0xFFFFu);
+    if (dst) dst[e - e0] = E.h_exp_dst[e];
+    if (kind) kind[e - e0] = (int)(E.h_exp_src[e] >> 16);
   }
   return (int)(e1 - e0);
 }
@@ -1380,7 +1448,7 @@ extern "C" void cfdp_finalize(void)
   if (E.have_device) {
     cudaDeviceSynchronize();
     if (E.comm) { g_nccl.CommDestroy(E.comm); E.comm = nullptr; }
-    cudaFree(E.d_var); cudaFree(E.d_grad); cudaFree(E.d_pvol); cudaFree(E.d_flux); E.d_flux = nullptr; cudaFree(E.d_fblob); cudaFree(E.d_ftiles); E.d_fblob = nullptr; E.d_ftiles = nullptr; cudaFree(E.d_blob); cudaFree(E.d_tiles); cudaFree(E.d_stage);
+    cudaFree(E.d_var); cudaFree(E.d_grad); cudaFree(E.d_pvol); cudaFree(E.d_hhalo); E.d_hhalo = nullptr; cudaFree(E.d_flux); E.d_flux = nullptr; cudaFree(E.d_fblob); cudaFree(E.d_ftiles); E.d_fblob = nullptr; E.d_ftiles = nullptr; cudaFree(E.d_blob); cudaFree(E.d_tiles); cudaFree(E.d_stage);
     cudaFree(E.d_loc_dst); cudaFree(E.d_loc_src); cudaFree(E.d_exp_off); cudaFree(E.d_exp_src); cudaFree(E.d_exp_dst); cudaFree(E.d_send_rows); cudaFree(E.d_recv_rows); cudaFree(E.d_sendbuf); cudaFree(E.d_recvbuf);
     for (int *p : E.d_rowmap) cudaFree(p);
   }
@@ -1407,7 +1475,7 @@ extern "C" void cfdp_finalize(void)
     delete d;
   }
   E.doms.clear(); E.d_rowmap.clear(); E.point_of_row.clear(); E.peers.clear(); E.send_rows_of.clear(); E.recv_rows_of.clear();
-  if (E.pipe.prof) { cudaFree(E.pipe.prof); E.pipe.prof = nullptr; }
+  if (E.pipe.prof) { cudaFree(E.pipe.prof); E.pipe.prof = nullptr; E.pipe4.prof = nullptr; }
   if (E.d_progress) { cudaFree(E.d_progress); E.d_progress = nullptr; }
   e2e_release();
 
@@ -1416,7 +1484,7 @@ extern "C" void cfdp_finalize(void)
   E.committed = false; E.planned = false; E.configured = false;
   E.h_exp_off.clear(); E.h_exp_src.clear(); E.h_exp_dst.clear(); E.d_exp_off = E.d_exp_src = E.d_exp_dst = nullptr;
   E.h_tiles.clear(); E.blob_base.clear(); E.h_loc_dst.clear(); E.h_loc_src.clear(); E.h_send_rows.clear(); E.h_recv_rows.clear();
-  E.max_nfaces = E.max_nloc = E.max_npts = 0; E.max_stage = 0; E.blob_bytes = 0; E.max_blob = 0; E.max_nhalo = 0; E.max_footprint = 0; E.flux_smem = 0; E.with_flux = 0; E.flux_alg_bytes = 0; E.h_ftiles.clear(); E.fblob_bytes = 0;
+  E.max_nfaces = E.max_nloc = E.max_npts = 0; E.max_stage = 0; E.blob_bytes = 0; E.max_blob = 0; E.max_nhalo = 0; E.max_footprint = 0; E.max_hvpv = 0; E.flux_smem = 0; E.with_flux = 0; E.flux_alg_bytes = 0; E.h_ftiles.clear(); E.fblob_bytes = 0;
   E.rows = E.ntiles = E.nbtiles = 0; E.nfaces = E.nown = E.nall = E.tile_faces = E.halo_refs = E.alg_bytes = 0;
   E.n_local = E.n_send = E.n_recv = 0; E.launches = 0; E.nprocs = 0; E.per_proc = 0;
 }

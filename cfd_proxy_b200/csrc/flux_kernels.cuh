@@ -86,7 +86,7 @@ psd_flux_tile_kernel(const TileDesc *__restrict__ tiles, const unsigned char *__
   const TileDesc td = tiles[blockIdx.x];
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int npts = td.npts, nhalo = td.nhalo, n_even = CFDP_HALO_BASE(npts);
-  const unsigned char *tb = blob + td.blob;
+  const unsigned char *tb = blob + td.blob_off();
   const uint32_t adj_src = flux_adj_src(td.halo_off, td.nhalo), adj_bytes = td.blob_bytes - adj_src;
   double *s_rows = reinterpret_cast<double *>(smem + flux_rows_off(td.blob_bytes, td.halo_off, td.nhalo));
 
@@ -197,7 +197,7 @@ psd_flux_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, 
   auto fetch_halo_rows = [&](int t) {
     if (t >= t_end) return;
     const TileDesc pd = s_tds[t - t_begin];
-    const uint32_t *g = reinterpret_cast<const uint32_t *>(blob + pd.blob + pd.halo_off);
+    const uint32_t *g = reinterpret_cast<const uint32_t *>(blob + pd.blob_off() + pd.halo_off);
 #pragma unroll
     for (int k = 0; k < CFDP_FLUX_HALO_PER_THREAD; k++) {
       const int h = tid + k * nthr;
@@ -209,7 +209,7 @@ psd_flux_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, 
   for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
     const TileDesc td = s_tds[t - t_begin];
     const int npts = td.npts, n_even = CFDP_HALO_BASE(npts);
-    const unsigned char *tb = blob + td.blob;
+    const unsigned char *tb = blob + td.blob_off();
     const uint32_t adj_src = flux_adj_src(td.halo_off, td.nhalo), adj_bytes = td.blob_bytes - adj_src;
     double *s_rows = reinterpret_cast<double *>(smem + flux_rows_off(td.blob_bytes, td.halo_off, td.nhalo));
     if (tid == 0) {

@@ -153,263 +153,368 @@ __device__ __forceinline__ void point_rows(int p, const uint32_t *__restrict__ e
   for (int k = 0; k < CNT * 3; k++) acc[k] = __dmul_rn(acc[k], inv_vol);
 }
 
-/* shared-memory stage of a tile: [blob | output rows (aliased)][half-var rows][volumes], each part 128-byte aligned;
- * the offsets depend on the tile, stage_bytes is the largest footprint of any tile */
-__host__ __device__ __forceinline__ uint32_t tile_var_off(uint32_t blob_bytes, uint32_t npts)
+/* ------------------------------------------------------------------------------------------------------------------
+ * Shared-memory stage of a tile (gg_tile_pipe_kernel), stage_bytes = the same for every tile of a launch:
+ *
+ *   [0, blob_bytes)                          the tile blob: normals | halo row list | ELL adjacency
+ *   [0, n_even * 168)                        the result rows, staged here once the face walk is over (aliases the blob)
+ *   [hvar_off, hvar_off + (n_even+nhalo)*56) half-var rows: own points, then the halo positions   } end aligned: the next
+ *   [pvol_off, stage_bytes)                  volumes of the own points                             } tile's rows never
+ *                                                                                                   } overlap staged rows
+ * The staged rows of warp w are bytes [5376 w, 5376 (w+1)) ("zone" w: 32 rows of 168 bytes): every warp stages, stores
+ * (one TMA bulk store per warp) and refills its own zone without a CTA-wide barrier.
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define CFDP_ROW_BYTES (NGRAD * 3 * 8)       /* 168 */
+#define CFDP_ZONE_BYTES (32 * CFDP_ROW_BYTES) /* 5376 */
+
+__host__ __device__ __forceinline__ uint32_t stage_hvar_bytes(uint32_t npts, uint32_t nhalo)
 {
-  const uint32_t out_bytes = npts * (NGRAD * 3 * 8);
-  return ((blob_bytes > out_bytes ? blob_bytes : out_bytes) + 127u) & ~127u;
+  return ((CFDP_HALO_BASE(npts) + nhalo) * (NGRAD * 8) + 127u) & ~127u;
 }
-__host__ __device__ __forceinline__ uint32_t tile_pvol_off(uint32_t blob_bytes, uint32_t npts, uint32_t nhalo)
+__host__ __device__ __forceinline__ uint32_t stage_pvol_bytes(uint32_t npts) { return (CFDP_HALO_BASE(npts) * 8 + 127u) & ~127u; }
+__host__ __device__ __forceinline__ uint32_t stage_pvol_off(uint32_t stage_bytes, uint32_t npts) { return stage_bytes - stage_pvol_bytes(npts); }
+__host__ __device__ __forceinline__ uint32_t stage_hvar_off(uint32_t stage_bytes, uint32_t npts, uint32_t nhalo)
 {
-  return tile_var_off(blob_bytes, npts) + (((CFDP_HALO_BASE(npts) + nhalo) * (NGRAD * 8) + 127u) & ~127u);
+  return stage_pvol_off(stage_bytes, npts) - stage_hvar_bytes(npts, nhalo);
 }
+/* bytes one tile needs: blob (or the staged rows, whichever is larger) + var rows + volumes */
 __host__ __device__ __forceinline__ uint32_t tile_footprint(uint32_t blob_bytes, uint32_t npts, uint32_t nhalo)
 {
-  return tile_pvol_off(blob_bytes, npts, nhalo) + ((CFDP_HALO_BASE(npts) * 8 + 127u) & ~127u);
+  const uint32_t out_bytes = CFDP_HALO_BASE(npts) * CFDP_ROW_BYTES;
+  return (((blob_bytes > out_bytes ? blob_bytes : out_bytes) + 127u) & ~127u) + stage_hvar_bytes(npts, nhalo) + stage_pvol_bytes(npts);
 }
+
+#define CFDP_EXP_BASES 10 /* export destinations: 0 = grad of this GPU, 1 = packed send buffer, 2 + k = grad of peer GPU k (CUDA IPC mapping) */
 struct PipeLayout {
   uint32_t stage_bytes;
-  int block_points;  /* threads per CTA (multiple of 32, >= largest tile) */
-  unsigned long long *prof; /* optional: SM cycles of thread 0 summed over tiles: [0] wait for data, [1] face walk, [2] rest of the tile, [4] tiles */
-  unsigned long long *progress; /* counts finished boundary tiles (tile index < nsignal): the early-send trigger the comm stream waits on */
+  int cstride, istride, maxcount;  /* CTA b walks tiles b*cstride + i*istride, i < maxcount (contiguous chunks: chunk,1,chunk; interleaved: 1,grid,inf) */
+  unsigned long long *prof;        /* optional: SM cycles of thread 0 summed over tiles: [0] wait for data, [1] face walk, [2] rest, [4] tiles */
+  unsigned long long *progress;    /* counts finished boundary tiles (tile index < nsignal): the early-send trigger the comm stream waits on */
   int nsignal;
-  int split_roles; /* warp 0 drives the bulk copies instead of gathering */
-  int tile_base;  /* global index of this launch's first tile */
-  int nexport;    /* global tiles [0, nexport) write their export rows (fused pack); 0 = off */
-  const uint32_t *exp_off, *exp_src, *exp_dst; /* per boundary tile: tile-local point -> grad row (bit 31 clear) or send-buffer slot (bit 31 set) */
-  double *sendbuf;
+  int tile_base;                   /* global index of this launch's first tile */
+  int nexport;                     /* global tiles [0, nexport) write their export rows (fused pack / direct halo stores); 0 = off */
+  const uint32_t *exp_off, *exp_src, *exp_dst; /* per boundary tile: (tile-local point | destination array << 16) -> row of that array */
+  double *exp_base[CFDP_EXP_BASES];
+  /* direct halo stores into peer memory: per boundary tile the (peer, rows) pairs it completes; the peer's arrival counter
+   * is bumped by the number of rows (threads.c:268-306: per-partner counters of finalised send points) */
+  const uint32_t *sig_off, *sig_ent;          /* ent = peer | rows << 4 */
+  unsigned long long *sig_flag[CFDP_EXP_BASES - 2];
 };
 
-__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes, uint64_t policy)
+__device__ __forceinline__ void bulk_s2g(void *gdst, uint32_t ssrc, uint32_t bytes, uint64_t policy)
 {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-               ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes), "l"(policy) : "memory");
+               ::"l"(gdst), "r"(ssrc), "r"(bytes), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-/* the bulk stores counted by n are complete (wait_group): publish them with one release reduction */
+__device__ __forceinline__ void bulk_wait_prev() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+/* the stores counted by n are complete: publish them with one release reduction */
 __device__ __forceinline__ void signal_progress(unsigned long long *ctr, int n)
 {
   asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(ctr), "l"((unsigned long long)n) : "memory");
 }
-__device__ __forceinline__ void bulk_wait_prev() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void signal_peer(unsigned long long *ctr, unsigned long long n)
+{
+  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(ctr), "l"(n) : "memory");
+}
+/* shared-memory accesses of the face walk by 32-bit shared address: the compiler neither rematerialises the
+ * (cluster-relative) base of the dynamic shared memory in the loop nor reorders them across the barriers */
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void bulk_g2s_a(uint32_t sdst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(sdst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async8_a(uint32_t sdst, const void *src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst), "l"(src) : "memory");
+}
+
+struct FaceOps { double n[3]; double w[NGRAD]; };
+/* operands of one adjacency entry: the face normal and the neighbour's half-var row */
+__device__ __forceinline__ void load_face_ops(uint32_t e, uint32_t a_nrm, uint32_t a_hv, FaceOps &o)
+{
+  const uint32_t an = a_nrm + 24u * ((e >> 16) & 0x7FFFu), aw = a_hv + (NGRAD * 8u) * (e & 0x7FFFu);
+#pragma unroll
+  for (int c = 0; c < 3; c++) o.n[c] = lds_f64(an + 8u * c);
+#pragma unroll
+  for (int q = 0; q < NGRAD; q++) o.w[q] = lds_f64(aw + 8u * q);
+}
+template <bool EXACT>
+__device__ __forceinline__ void face_update(const FaceOps &o, uint32_t e, const double (&hv)[NGRAD], double (&acc)[NGRAD * 3])
+{
+  const uint32_t sb = e & 0x80000000u;        /* this point is p1 of the face: grad[p1] -= n*val (gradients.c:101-105) */
+  const double nx = flip_sign(o.n[0], sb), ny = flip_sign(o.n[1], sb), nz = flip_sign(o.n[2], sb);
+#pragma unroll
+  for (int q = 0; q < NGRAD; q++) {
+    if (EXACT) {
+      const double val = __dadd_rn(hv[q], o.w[q]);                      /* == 0.5*(var[p0]+var[p1]), gradients.c:77 */
+      acc[3 * q + 0] = __dadd_rn(acc[3 * q + 0], __dmul_rn(nx, val));
+      acc[3 * q + 1] = __dadd_rn(acc[3 * q + 1], __dmul_rn(ny, val));
+      acc[3 * q + 2] = __dadd_rn(acc[3 * q + 2], __dmul_rn(nz, val));
+    } else {
+      const double val = hv[q] + o.w[q];
+      acc[3 * q + 0] = fma(nx, val, acc[3 * q + 0]);
+      acc[3 * q + 1] = fma(ny, val, acc[3 * q + 1]);
+      acc[3 * q + 2] = fma(nz, val, acc[3 * q + 2]);
+    }
+  }
+}
 
 /*
- * Two CTAs per SM, each owning one shared-memory stage and a chunk of consecutive tiles.  Timeline of a tile t:
- *   wait(mbarrier)            all of tile t has landed (bulk copies + halo gather); then the halo row list of tile
- *                             t+1 is prefetched (16-byte cp.async) and lands during the walk
- *   face walk                 one thread per point, 21 sums in registers
- *   S1 barrier                normals / adjacency / var of tile t are dead
- *   stage the rows of tile t  into the head of the stage (transposed through shared memory)
- *   S2 barrier
- *   TMA bulk store of the rows (one instruction); boundary tiles also write their export rows (fused pack)
- *   early fetch of tile t+1   while the TMA engine drains the staged rows: var rows, volumes, blob tail (bulk copies)
- *                             and the halo gather (8-byte cp.async): everything that does not overlap the staged rows
- *   head of tile t+1's blob   once the store has read shared memory.  While this CTA waits, the other CTA computes.
- * No thread ever blocks on a global load: HBM is touched only by asynchronous copies.
+ * Packed halo rows.  The half-var rows of a tile's halo points (end points of its faces outside the tile) are not
+ * gathered by the gradient kernel: a row-wise gather through the load/store unit (8-byte cp.async) cost 20 % of the kernel
+ * (measured: 1.81 -> 1.45 ms on 16.8 M points without it), because every warp-level copy of scattered 56-byte rows takes
+ * about one L2 round trip to issue while the other CTA of the SM keeps the unit busy with its face walk.  Instead,
+ * whenever var is uploaded this kernel writes, per tile, a contiguous copy of its halo rows in the order of the tile's
+ * shared-memory halo positions (halo_pack_kernel); the gradient kernel fetches the block with ONE TMA bulk copy.
+ * Price: 65 bytes per point of extra DRAM reads per iteration (the copies are not shared between tiles).
+ */
+__global__ void __launch_bounds__(256)
+halo_pack_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsigned char *__restrict__ blob,
+                 const double *__restrict__ hvar, double *__restrict__ hhalo)
+{
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const TileDesc td = tiles[t];
+    const uint32_t *hrows = reinterpret_cast<const uint32_t *>(blob + td.blob_off() + td.halo_off);
+    double *dst = hhalo + (size_t)td.hrow0 * NGRAD;
+    const int nw = (int)td.nhalo * NGRAD;
+    for (int k = threadIdx.x; k < nw; k += blockDim.x) {
+      const int r = k / NGRAD;
+      const uint32_t row = __ldg(hrows + r);
+      dst[k] = row != 0xFFFFFFFFu ? __ldg(hvar + (size_t)row * NGRAD + (k - r * NGRAD)) : 0.0; /* unused positions: zeros */
+    }
+  }
+}
+
+/*
+ * The production kernel.  Two CTAs per SM, each owning one shared-memory stage and walking a sequence of tiles.
+ * Timeline of tile t in one CTA:
+ *   B0   barrier (the descriptor prefetched during the previous walk is visible) + mbarrier wait: the bulk copies of
+ *        tile t (blob, own var rows, packed halo rows, volumes) have landed.
+ *   walk one thread per own point: its adjacency column in the reference's face order, 21 sums in registers; the
+ *        operands of step j+1 are loaded while step j is computed; padding entries are turned into exact zeros
+ *        (zero normal, the point itself as neighbour), so the loop has no data-dependent branch.
+ *   S1   barrier: normals / adjacency / var rows of tile t are dead.
+ *        early fetch of tile t+1 (thread 0, four bulk copies): everything that does not overlap the staged rows --
+ *        blob tail, own var rows, halo rows, volumes -- is requested NOW, before the rows are staged.
+ *   per warp, no CTA barrier: stage the 32 rows of the warp (zone w), fence.proxy.async, lane 0 issues one TMA bulk
+ *        store for the zone, waits until the store has READ the zone and refills it at once with the bytes of tile
+ *        t+1's blob that live there (late fetch).  Boundary tiles also write their export rows (fused pack, or direct
+ *        stores into the ghost rows of a peer GPU) between two barriers, and bump the arrival counters.
+ * No thread ever touches global memory with a load: HBM is read by TMA bulk copies only.
  */
 template <bool EXACT>
 __global__ void __launch_bounds__(CFDP_MAX_TILE_POINTS, 2)
-gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, const unsigned char *__restrict__ blob,
-                    const double *__restrict__ hvar, const double *__restrict__ pvol, double *__restrict__ grad, PipeLayout L)
+gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsigned char *__restrict__ blob,
+                    const double *__restrict__ hvar, const double *__restrict__ hhalo, const double *__restrict__ pvol,
+                    double *__restrict__ grad, PipeLayout L)
 {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full;
-  __shared__ TileDesc s_tds[CFDP_MAX_CHUNK];   /* descriptors of this CTA's tiles */
-  __shared__ __align__(16) uint32_t s_hidx[CFDP_MAX_HALO_POS]; /* halo row list of the tile being prefetched */
-  __shared__ uint32_t s_exp[2 * CFDP_MAX_EXPORT];               /* this tile's export list: sources, then destinations */
-  __shared__ uint32_t s_exp_off[CFDP_MAX_CHUNK + 1];            /* export list bounds of this CTA's tiles */
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int t_begin = blockIdx.x * chunk;
-  const int t_end = min(t_begin + chunk, ntiles);
-  if (t_begin >= t_end) return;
-  {
-    const int nw = (t_end - t_begin) * (int)(sizeof(TileDesc) / 4);
-    const uint32_t *g = reinterpret_cast<const uint32_t *>(tiles + t_begin);
-    uint32_t *d = reinterpret_cast<uint32_t *>(s_tds);
-    for (int i = tid; i < nw; i += nthr) d[i] = __ldg(g + i);
-    for (int i = tid; i <= t_end - t_begin; i += nthr) {
-      const int gt = L.tile_base + t_begin + i;
-      s_exp_off[i] = gt <= L.nexport ? __ldg(L.exp_off + gt) : 0u; /* exp_off has nexport + 1 entries */
+  __shared__ __align__(16) TileDesc s_desc[4];                  /* ring: descriptors of tiles i, i+1, i+2 of this CTA */
+  __shared__ uint32_t s_eoff[4][2];                              /* ring: export list bounds of those tiles */
+  __shared__ uint32_t s_exp[2 * CFDP_MAX_EXPORT];                /* this tile's export list: sources, then destinations */
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  /* this CTA's tiles: t(i) = first + i*istride, i < count */
+  const long long first = (long long)blockIdx.x * L.cstride;
+  if (first >= ntiles) return;
+  int count = (int)((ntiles - first + L.istride - 1) / L.istride);
+  if (count > L.maxcount) count = L.maxcount;
+  const uint32_t sbase = smem_u32(smem), bar = smem_u32(&full);
+  const uint64_t pol_stream = l2_policy_evict_first();
+  auto tile_of = [&](int i) { return (int)(first + (long long)i * L.istride); };
+
+  /* descriptor (and export bounds) of this CTA's tile i -> ring slot i & 3, asynchronously */
+  auto prefetch_desc = [&](int i) {
+    if (i < count) {
+      const int t = tile_of(i);
+      if (tid < 8) cp_async4(reinterpret_cast<uint32_t *>(&s_desc[i & 3]) + tid, reinterpret_cast<const uint32_t *>(tiles + t) + tid);
+      else if (tid < 10) {
+        const int gt = L.tile_base + t + (tid - 8);
+        if (gt <= L.nexport && L.nexport > 0) cp_async4(&s_eoff[i & 3][tid - 8], L.exp_off + gt); /* exp_off has nexport + 1 entries */
+      }
     }
-  }
+  };
+  /* thread 0: bulk copies of tile pd: blob bytes [lo, blob_bytes), own var rows, packed halo rows, volumes;
+   * announces ALL bytes of the tile (the rest of the blob follows from the warps' late fetches) */
+  auto bulk_early = [&](const TileDesc &pd, uint32_t lo) {
+    const uint32_t n_even = CFDP_HALO_BASE((uint32_t)pd.npts);
+    const uint32_t nv = n_even * (NGRAD * 8), nh = (uint32_t)pd.nhalo * (NGRAD * 8), np = n_even * 8;
+    const uint32_t a_hv = sbase + stage_hvar_off(L.stage_bytes, pd.npts, pd.nhalo);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(pd.blob_bytes + nv + nh + np) : "memory");
+    if (lo < pd.blob_bytes) bulk_g2s_a(sbase + lo, blob + pd.blob_off() + lo, pd.blob_bytes - lo, bar, pol_stream);
+    bulk_g2s_a(a_hv, hvar + (size_t)pd.row0 * NGRAD, nv, bar, pol_stream);
+    if (nh) bulk_g2s_a(a_hv + nv, hhalo + (size_t)pd.hrow0 * NGRAD, nh, bar, pol_stream);
+    bulk_g2s_a(sbase + stage_pvol_off(L.stage_bytes, pd.npts), pvol + pd.row0, np, bar, pol_stream);
+  };
+
+  /* prologue: descriptors of tiles 0, 1 (2 follows asynchronously), all of tile 0 */
   if (tid == 0) {
-    mbar_init(&full, (uint32_t)nthr + 1);
+    mbar_init(&full, 1);
     fence_mbar_init();
   }
-  unsigned char *const st = smem;
-  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-
-  /* halo row list of tile t (part of its blob) -> s_hidx, asynchronously */
-  auto stage_pf_index = [&](int t) {
-    if (t < t_end) {
-      const TileDesc pd = s_tds[t - t_begin];
-      const uint4 *g = reinterpret_cast<const uint4 *>(blob + pd.blob + pd.halo_off);
-      const int n16 = (int)pd.nhalo >> 2; /* nhalo (positions) is a multiple of 16 */
-      for (int i = tid; i < n16; i += nthr) cp_async16(&s_hidx[4 * i], g + i);
-    }
-    cp_async_commit();
-  };
-  /* thread 0: announce the bytes of tile t and start its bulk copies for blob bytes [lo, hi) (+ var rows and volumes) */
-  auto bulk_part = [&](const TileDesc &pd, uint32_t lo, uint32_t hi, bool with_var, bool announce) {
-    const uint32_t n_even = CFDP_HALO_BASE((uint32_t)pd.npts);
-    const uint32_t nv = n_even * (NGRAD * 8), np = n_even * 8;
-    if (announce) mbar_arrive_expect_tx(&full, pd.blob_bytes + nv + np);
-    if (hi > lo) bulk_g2s_hint(st + lo, blob + pd.blob + lo, hi - lo, &full, pol_stream);
-    if (with_var) {
-      bulk_g2s_hint(st + tile_var_off(pd.blob_bytes, pd.npts), hvar + (size_t)pd.row0 * NGRAD, nv, &full, pol_keep);
-      bulk_g2s_hint(st + tile_pvol_off(pd.blob_bytes, pd.npts, pd.nhalo), pvol + pd.row0, np, &full, pol_stream);
-    }
-  };
-  /* all threads: hvar rows of the halo points, consecutive lanes = consecutive words of a row.  (Moving a row as
-   * 16-byte pieces needs the halo position to share the parity of the device row; measured slower: the parity
-   * constraint costs more bank conflicts in the face walk than the shorter gather saves.) */
-  auto gather_halo = [&](const TileDesc &pd, int first, int stride) { /* first < 0: this thread only arrives */
-    double *vs = reinterpret_cast<double *>(st + tile_var_off(pd.blob_bytes, pd.npts)) + (size_t)CFDP_HALO_BASE((uint32_t)pd.npts) * NGRAD;
-    const int nw = (int)pd.nhalo * NGRAD;
-    for (int i = first >= 0 ? first : nw; i < nw; i += stride) {
-      const int r = i / NGRAD;
-      const uint32_t row = s_hidx[r];
-      if (row != 0xFFFFFFFFu) cp_async8(vs + i, hvar + (size_t)row * NGRAD + (i - r * NGRAD));
-    }
-    /* the arrival is issued by whole, converged warps only: issued under divergence (lane 0 of warp 0 busy with the
-     * bulk copies, or lanes leaving the loop above at different trips) the phase was observed to complete early */
-    __syncwarp();
-    cp_async_mbar_arrive_noinc(&full);
-  };
-
-  __syncthreads(); /* descriptors and mbarrier visible */
-  stage_pf_index(t_begin);
-  cp_async_wait_all();
+  prefetch_desc(0); prefetch_desc(1);
+  cp_async_commit(); cp_async_wait_all();
   __syncthreads();
-  {
-    const TileDesc pd = s_tds[0];
-    if (tid == 0) bulk_part(pd, 0, pd.blob_bytes, true, true);
-    gather_halo(pd, tid, nthr);
-  }
-  __syncthreads(); /* s_hidx may be refilled */
-  /* split roles (CFDP_SPLIT_ROLES=0 turns it off): warp 0 does not gather, its lane 0 drives the bulk store and the
-   * bulk copies of the next tile, so that the head of the next blob is requested the moment the store has drained
-   * the staged rows (4 % faster: 1.82 -> 1.75 ms on 16.8 M points) */
-  const bool split_roles = nthr >= 128 && L.split_roles == 1;
-  const int g_first = split_roles ? (tid >= 32 ? tid - 32 : -1) : tid, g_stride = split_roles ? nthr - 32 : nthr;
+  if (tid == 0) bulk_early(s_desc[0], 0);
 
-  int pending_sig = 0; /* thread 0: boundary tiles stored but not yet signalled */
-  for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
-    const bool has_next = t + 1 < t_end;
-    const TileDesc td = s_tds[t - t_begin];
-    const int npts = td.npts, nhalo = td.nhalo;
-    double *s_nrm = reinterpret_cast<double *>(st);
-    const double *s_hvar = reinterpret_cast<const double *>(st + tile_var_off(td.blob_bytes, td.npts));
-    const double *s_pvol = reinterpret_cast<const double *>(st + tile_pvol_off(td.blob_bytes, td.npts, td.nhalo));
-    const uint32_t *ell0 = reinterpret_cast<const uint32_t *>(st + td.halo_off + ((nhalo * 4 + 15) & ~15));
+  int pending_sig = 0; /* boundary tiles of this CTA stored but not yet reported (uniform over the CTA) */
+  for (int i = 0; i < count; ++i) {
+    const int t = tile_of(i);
+    const bool has_next = i + 1 < count;
     long long c0 = 0, c1 = 0, c2 = 0;
     if (L.prof && tid == 0) c0 = clock64();
-    mbar_wait(&full, (uint32_t)it & 1u);
+    cp_async_wait_all();
+    __syncthreads();                    /* B0: the prefetched descriptor of tile i+1 is visible to every thread */
+    mbar_wait(&full, (uint32_t)i & 1u); /* the bulk copies have landed */
     if (L.prof && tid == 0) c1 = clock64();
-    /* the phase completes only after every thread has arrived, i.e. is done reading s_hidx for this tile's halo
-     * gather: the list of the next tile may now be fetched; it lands during the face walk */
-    stage_pf_index(t + 1);
+    const TileDesc td = s_desc[i & 3];
+    const int npts = td.npts;
+    prefetch_desc(i + 2);
+    cp_async_commit();
 
     double acc[NGRAD * 3];
+#pragma unroll
+    for (int k = 0; k < NGRAD * 3; k++) acc[k] = 0.0;
     const bool active = tid < npts;
     if (active) {
-      const double inv_vol = __ddiv_rn(1.0, s_pvol[tid]);                 /* gradients.c:138 */
-      point_rows<EXACT, 0, NGRAD>(tid, ell0, td.npad, td.maxdeg, s_nrm, s_hvar, inv_vol, acc);
+      const uint32_t a_hv = sbase + stage_hvar_off(L.stage_bytes, td.npts, td.nhalo);
+      const uint32_t a_ell = sbase + td.halo_off + (((uint32_t)td.nhalo * 4u + 15u) & ~15u) + 4u * tid;
+      const uint32_t pitch = 4u * td.npad;
+      const int maxdeg = td.maxdeg;
+      const uint32_t pad_e = (uint32_t)tid | ((uint32_t)td.zslot << 16); /* the point itself across a zero normal */
+      double hv[NGRAD];
+#pragma unroll
+      for (int q = 0; q < NGRAD; q++) hv[q] = lds_f64(a_hv + (NGRAD * 8u) * tid + 8u * q);
+      const double vol = lds_f64(sbase + stage_pvol_off(L.stage_bytes, td.npts) + 8u * tid);
+      if (maxdeg > 0) {
+        /* adjacency entry of step j: raw word (steps beyond the column re-read the last row), then padding entries
+         * and steps beyond the column become the point itself across the zero normal: a contribution of exactly +-0 */
+        auto raw = [&](int j) { return lds_u32(a_ell + pitch * (uint32_t)min(j, maxdeg - 1)); };
+        auto fix = [&](uint32_t r, int j) { return (j < maxdeg && r != CFDP_ADJ_PAD) ? r : pad_e; };
+        FaceOps A, B;
+        uint32_t ea = fix(raw(0), 0), eb = fix(raw(1), 1);
+        load_face_ops(ea, sbase, a_hv, A);
+        for (int j = 0; j < maxdeg; j += 2) {
+          const uint32_t ra = raw(j + 2), rb = raw(j + 3);   /* two steps ahead: address arithmetic off the critical path */
+          load_face_ops(eb, sbase, a_hv, B);
+          face_update<EXACT>(A, ea, hv, acc);
+          ea = fix(ra, j + 2);
+          load_face_ops(ea, sbase, a_hv, A);
+          face_update<EXACT>(B, eb, hv, acc);
+          eb = fix(rb, j + 3);
+        }
+      }
+      const double inv_vol = __ddiv_rn(1.0, vol);                        /* gradients.c:138 */
+#pragma unroll
+      for (int k = 0; k < NGRAD * 3; k++) acc[k] = __dmul_rn(acc[k], inv_vol);
     }
-    cp_async_wait_all(); /* this thread's share of the next halo row list is in s_hidx */
     __syncthreads();     /* S1: normals, adjacency and var of this tile are dead */
     if (L.prof && tid == 0) c2 = clock64();
 
-    /* the output rows are staged in [0, out_end) and leave through one bulk store; while the TMA engine reads them,
-     * whatever of the next tile lives beyond out_end is fetched; the head of its blob follows when the read is done */
-    const uint32_t out_rows = CFDP_HALO_BASE((uint32_t)npts);
-    const uint32_t out_end = (out_rows * (NGRAD * 3 * 8) + 127u) & ~127u;
+    const uint32_t n_even = CFDP_HALO_BASE((uint32_t)npts);
+    const uint32_t out_cover = n_even * CFDP_ROW_BYTES;    /* bytes [0, out_cover) hold the staged rows */
     TileDesc nd = td;
-    bool early = false;
-    if (has_next) {
-      nd = s_tds[t + 1 - t_begin];
-      early = tile_var_off(nd.blob_bytes, nd.npts) >= out_end;
+    if (has_next) { /* early fetch of the next tile: runs under the staging / store of this one */
+      nd = s_desc[(i + 1) & 3];
+      if (tid == 0) bulk_early(nd, out_cover < nd.blob_bytes ? out_cover : nd.blob_bytes);
     }
-    /* export list of this tile (fused pack), fetched asynchronously while the rows are being staged */
+    /* export list of this tile, fetched asynchronously while the rows are being staged */
     const int gt = L.tile_base + t;
-    const uint32_t e0 = gt < L.nexport ? s_exp_off[t - t_begin] : 0u;
-    const int nexp = gt < L.nexport ? (int)(s_exp_off[t - t_begin + 1] - e0) : 0;
+    const uint32_t e0 = gt < L.nexport ? s_eoff[i & 3][0] : 0u;
+    const int nexp = gt < L.nexport ? (int)(s_eoff[i & 3][1] - e0) : 0;
     const bool exp_in_smem = nexp > 0 && nexp <= CFDP_MAX_EXPORT;
     if (exp_in_smem) {
-      for (int i = tid; i < nexp; i += nthr) {
-        cp_async4(&s_exp[i], L.exp_src + e0 + i);
-        cp_async4(&s_exp[CFDP_MAX_EXPORT + i], L.exp_dst + e0 + i);
+      for (int k = tid; k < nexp; k += nthr) {
+        cp_async4(&s_exp[k], L.exp_src + e0 + k);
+        cp_async4(&s_exp[CFDP_MAX_EXPORT + k], L.exp_dst + e0 + k);
       }
-      cp_async_commit();
     }
-    if (active) {
-      double *o = s_nrm + tid * (NGRAD * 3);
-#pragma unroll
-      for (int k = 0; k < NGRAD * 3; k++) o[k] = acc[k];
-    }
-    fence_proxy_async(); /* the staged rows (generic proxy) become visible to the bulk store (async proxy) */
-    cp_async_wait_all(); /* export list */
-    __syncthreads();     /* S2 */
+    cp_async_commit();
     long long q1 = 0, q2 = 0, q3 = 0;
     if (L.prof && tid == 0) q1 = clock64();
-    if (tid == 0) {
-      bulk_s2g(grad + (size_t)td.row0 * (NGRAD * 3), s_nrm, out_rows * (NGRAD * 3 * 8), pol_stream); /* rows beyond npts are alignment padding */
-      bulk_commit();
+
+    /* stage this warp's rows; rows npts .. n_even-1 are alignment padding of the tile (zeros) */
+    const uint32_t rows_w = (uint32_t)(32 * warp) < n_even ? min(32u, n_even - 32u * warp) : 0u;
+    if ((uint32_t)tid < n_even) {
+      const uint32_t o = sbase + CFDP_ROW_BYTES * (uint32_t)tid;
+#pragma unroll
+      for (int k = 0; k < NGRAD * 3; k++) sts_f64(o + 8u * k, acc[k]);
     }
-    if (nexp > 0) {
-      /* fused pack (threads.c:187-249, :791-813): the rows of this tile that other domains need go straight from the
-       * staged rows to the packed send buffer, or to the ghost rows of a domain hosted on this GPU */
-      const int nw = nexp * (NGRAD * 3);
-      for (int i = tid; i < nw; i += nthr) {
-        const int r = i / (NGRAD * 3), c = i - r * (NGRAD * 3);
-        const uint32_t src = exp_in_smem ? s_exp[r] : __ldg(L.exp_src + e0 + r);
-        const uint32_t dst = exp_in_smem ? s_exp[CFDP_MAX_EXPORT + r] : __ldg(L.exp_dst + e0 + r);
-        double *base = (dst & 0x80000000u) ? L.sendbuf : grad;
-        base[(size_t)(dst & 0x7FFFFFFFu) * (NGRAD * 3) + c] = s_nrm[src * (NGRAD * 3) + c];
+    if (rows_w) {
+      fence_proxy_async(); /* the staged rows (generic proxy) become visible to the bulk store (async proxy) */
+      __syncwarp();
+      if (lane == 0) {
+        bulk_s2g(grad + ((size_t)td.row0 + 32u * warp) * (NGRAD * 3), sbase + CFDP_ZONE_BYTES * (uint32_t)warp, rows_w * CFDP_ROW_BYTES, pol_stream);
+        bulk_commit();
       }
-      __syncthreads(); /* the staged rows have been read by every thread (and ordered before thread 0's release below) */
-    }
-    if (has_next && early) { /* runs while the bulk store drains the staged rows */
-      if (tid == 0) bulk_part(nd, out_end < nd.blob_bytes ? out_end : nd.blob_bytes, nd.blob_bytes, true, true);
-      gather_halo(nd, g_first, g_stride);
     }
     if (L.prof && tid == 0) q2 = clock64();
-    if (tid == 0) {
-      bulk_wait_read();      /* shared memory may be overwritten */
-      if (L.prof) q3 = clock64();
-      /* boundary tiles: their rows may be packed / copied by the exchange as soon as every boundary tile has retired
-       * (the reference's finalised-send-point counters, threads.c:268-306).  A CTA reports its boundary tiles in
-       * one go, when it retires or reaches its first interior tile: nobody waits for a write to reach global memory. */
-      if (pending_sig && t >= L.nsignal) {   /* first interior tile of this CTA: flush the signals of its boundary tiles */
-        bulk_wait_prev();    /* every store group but the one just committed is complete */
-        signal_progress(L.progress, pending_sig);
-        pending_sig = 0;
+    if (nexp > 0) {
+      /* fused pack (threads.c:187-249, :791-813) / direct halo stores: the rows of this tile that other domains need go
+       * straight from the staged rows to their consumers: the packed send buffer, the ghost rows of a domain hosted on
+       * this GPU, or the ghost rows of a domain on a peer GPU (CUDA IPC mapping, stores over NVLink) */
+      cp_async_wait_all(); /* the export list (and the descriptor prefetch) */
+      __syncthreads();
+      const double *s_out = reinterpret_cast<const double *>(smem);
+      const int nw = nexp * (NGRAD * 3);
+      for (int k = tid; k < nw; k += nthr) {
+        const int r = k / (NGRAD * 3), c = k - r * (NGRAD * 3);
+        const uint32_t sk = exp_in_smem ? s_exp[r] : __ldg(L.exp_src + e0 + r);     /* tile-local point | destination array << 16 */
+        const uint32_t dst = exp_in_smem ? s_exp[CFDP_MAX_EXPORT + r] : __ldg(L.exp_dst + e0 + r);
+        L.exp_base[sk >> 16][(size_t)dst * (NGRAD * 3) + c] = s_out[(sk & 0xFFFFu) * (NGRAD * 3) + c];
       }
-      if (t < L.nsignal) pending_sig++;
+      __syncthreads(); /* the staged rows have been read by every thread; the stores are ordered before thread 0's releases */
+      if (tid == 0 && L.sig_off) {
+        const uint32_t s0 = __ldg(L.sig_off + gt), s1 = __ldg(L.sig_off + gt + 1);
+        if (s1 > s0) {
+          __threadfence_system();
+          for (uint32_t s = s0; s < s1; s++) {
+            const uint32_t ent = __ldg(L.sig_ent + s);
+            signal_peer(L.sig_flag[ent & 15u], (unsigned long long)(ent >> 4));
+          }
+        }
+      }
+    }
+    if (rows_w && lane == 0) {
+      bulk_wait_read();      /* the zone may be overwritten: late fetch of the next tile's bytes that live in it */
+      if (L.prof && tid == 0) q3 = clock64();
       if (has_next) {
-        if (early) bulk_part(nd, 0, out_end < nd.blob_bytes ? out_end : nd.blob_bytes, false, false);
-        else bulk_part(nd, 0, nd.blob_bytes, true, true);
+        const uint32_t lo = CFDP_ZONE_BYTES * (uint32_t)warp, hi = min(min(lo + rows_w * CFDP_ROW_BYTES, out_cover), (uint32_t)nd.blob_bytes);
+        if (lo < hi) bulk_g2s_a(sbase + lo, blob + nd.blob_off() + lo, hi - lo, bar, pol_stream);
       }
     }
-    if (has_next && !early) { /* rare (a much smaller tile follows): its var rows overlap the staged rows */
+    /* boundary tiles: their rows may be consumed by the exchange as soon as every boundary tile has retired (the
+     * reference's finalised-send-point counters, threads.c:268-306).  A CTA reports its boundary tiles in one go,
+     * when it reaches its first interior tile or retires: nobody waits for a write to reach global memory. */
+    if (pending_sig && t >= L.nsignal) {
+      if (lane == 0) { /* every store group of this warp but the one just committed (if any) is complete */
+        if (rows_w) bulk_wait_prev(); else bulk_wait_all();
+        fence_proxy_async_all();
+      }
       __syncthreads();
-      gather_halo(nd, tid, nthr);
-      __syncthreads();
+      if (tid == 0) signal_progress(L.progress, pending_sig);
+      pending_sig = 0;
     }
+    if (t < L.nsignal) pending_sig++;
     if (L.prof && tid == 0) {
       const long long c3 = clock64();
       atomicAdd(L.prof + 0, (unsigned long long)(c1 - c0)); atomicAdd(L.prof + 1, (unsigned long long)(c2 - c1));
       atomicAdd(L.prof + 2, (unsigned long long)(c3 - c2)); atomicAdd(L.prof + 4, 1ull);
+      /* [5] early fetch issue, [6] staging + store issue, [7] exports + wait until the store has read the zone */
       atomicAdd(L.prof + 5, (unsigned long long)(q1 - c2)); atomicAdd(L.prof + 6, (unsigned long long)(q2 - q1)); atomicAdd(L.prof + 7, (unsigned long long)(q3 - q2));
-      /* [5] staging up to S2, [6] store issue + exports + early fetch, [7] wait for the store to have read shared memory */
     }
   }
-  if (tid == 0 && pending_sig) {
-    bulk_wait_all();
-    signal_progress(L.progress, pending_sig);
+  if (pending_sig) {
+    if (lane == 0) { bulk_wait_all(); fence_proxy_async_all(); }
+    __syncthreads();
+    if (tid == 0) signal_progress(L.progress, pending_sig);
   }
 }
 
@@ -424,7 +529,7 @@ gg_tile_kernel(const TileDesc *__restrict__ tiles, const unsigned char *__restri
   double *s_r0 = reinterpret_cast<double *>(smem_raw);  /* normals, later the output rows */
   double *s_var = s_r0 + region0_doubles;               /* [npts(even) + nhalo][7] */
   const TileDesc td = tiles[blockIdx.x];
-  const unsigned char *tb = blob + td.blob;
+  const unsigned char *tb = blob + td.blob_off();
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int npts = td.npts, nhalo = td.nhalo, nfaces = td.nfaces;
   const int n_even = CFDP_HALO_BASE(npts);

@@ -88,7 +88,7 @@ struct TileBuilder {
   size_t footprint(int np_, int nf_, int nh_, int md_) const
   {
     const uint32_t npad = (uint32_t)align_up((size_t)np_, 32);
-    nf_ = (int)align_up((size_t)nf_ + (size_t)opt.slack_slots, 16); nh_ = (int)align_up((size_t)nh_ + (size_t)opt.slack_halo, 16);
+    nf_ = (int)align_up((size_t)nf_ + 1 + (size_t)opt.slack_slots, 16); nh_ = (int)align_up((size_t)nh_ + (size_t)opt.slack_halo, 16);
     return align_up(std::max(blob_size((uint32_t)nf_, (uint32_t)nh_, (uint32_t)md_, npad), (size_t)np_ * CFDP_DIM2 * 8), 128) +
            align_up((size_t)(CFDP_HALO_BASE(np_) + nh_) * NGRAD * 8, 128) + align_up((size_t)CFDP_HALO_BASE(np_) * 8, 128);
   }
@@ -420,7 +420,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
    * (ids in discovery order; the shared-memory slot is chosen later) */
   std::vector<int> eslot(g.face.size(), -1);
   std::vector<int> tnh((size_t)ntiles, 0), tmaxdeg((size_t)ntiles, 0);
-  out.tile_nslots.assign((size_t)ntiles, 0); out.tile_nhpos.assign((size_t)ntiles, 0);
+  out.tile_nslots.assign((size_t)ntiles, 0); out.tile_nhpos.assign((size_t)ntiles, 0); out.tile_zslot.assign((size_t)ntiles, 0);
   const int nthreads = omp_get_max_threads();
   std::vector<std::vector<int>> lmap_t((size_t)nthreads);
   out.tile_face_off.assign((size_t)ntiles + 1, 0); out.tile_halo_off.assign((size_t)ntiles + 1, 0);
@@ -454,7 +454,8 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
       out.tile_nfaces[k] = nf; tnh[k] = nh; tmaxdeg[k] = md;
       /* shared-memory positions: 16 residue classes of equal size, so that slots / rows can be placed by bank */
       /* a little slack lets the bank placement avoid forced collisions when a class fills up */
-      out.tile_nslots[k] = (int)align_up((size_t)nf + (size_t)opt.slack_slots, 16); out.tile_nhpos[k] = (int)align_up((size_t)nh + (size_t)opt.slack_halo, 16);
+      /* + 1: at least one slot stays unused, its normal is zero (TileDesc::zslot) */
+      out.tile_nslots[k] = (int)align_up((size_t)nf + 1 + (size_t)opt.slack_slots, 16); out.tile_nhpos[k] = (int)align_up((size_t)nh + (size_t)opt.slack_halo, 16);
       ASSERT(out.tile_nslots[k] <= 32767 && n + 1 + out.tile_nhpos[k] <= 65534);
     }
   }
@@ -704,6 +705,14 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
       place_all(tile_ents, deg, md, nh, nf, hpos_of, nhpos, slot_of, nslots);
 
       /* ---- emit */
+      {
+        std::vector<unsigned char> used_slot((size_t)nslots, 0);
+        for (int f = 0; f < nf; f++) used_slot[(size_t)slot_of[f]] = 1;
+        int z = nslots - 1;
+        while (z >= 0 && used_slot[(size_t)z]) z--;
+        ASSERT(z >= 0);
+        out.tile_zslot[k] = z;
+      }
       for (int f = 0; f < nf; f++) {
         const int sl = slot_of[f], gf = fids[f];
         ASSERT(sl >= 0 && sl < nslots);

@@ -248,8 +248,9 @@ class Session:
         buf = np.zeros(max(int(n), 1), np.uint8)
         self.lib.cfdp_get_tile_blob(C.byref(d.sd), t, 1 if flux else 0, desc, buf.ctypes.data_as(C.POINTER(C.c_ubyte)), int(n))
         row0, npts, nhalo, nfaces, maxdeg, npad, nbytes, halo_off = (int(x) for x in desc)
+        nfaces, zslot = nfaces & 0xFFFF, nfaces >> 16
         adj_off = halo_off + (nhalo * 4 + 15) // 16 * 16
-        return dict(row0=row0, npts=npts, nhalo=nhalo, nfaces=nfaces, maxdeg=maxdeg, npad=npad, bytes=nbytes,
+        return dict(row0=row0, npts=npts, nhalo=nhalo, nfaces=nfaces, zslot=zslot, maxdeg=maxdeg, npad=npad, bytes=nbytes,
                     normals=buf[:nfaces * 24].view(np.float64).reshape(nfaces, 3),
                     halo_rows=buf[halo_off:halo_off + nhalo * 4].view(np.uint32),
                     ell=buf[adj_off:adj_off + maxdeg * npad * 4].view(np.uint32).reshape(maxdeg, npad))

@@ -122,7 +122,7 @@ EXPORTED = [
     "cfdp_nc_open", "cfdp_nc_close", "cfdp_nc_strerror", "cfdp_nc_inq_dimid", "cfdp_nc_inq_dimlen",
     "cfdp_nc_inq_varid", "cfdp_nc_get_var_int", "cfdp_nc_get_var_double",
     "cfdp_configure", "cfdp_init_communication_domain", "cfdp_nccl_get_unique_id", "cfdp_nccl_init",
-    "cfdp_commit", "cfdp_plan", "cfdp_set_int_exchange", "cfdp_get_peer_plan", "cfdp_get_exchange_entry", "cfdp_get_tile_exports", "cfdp_get_row_owner", "cfdp_var_to_device", "cfdp_grad_to_host", "cfdp_set_resident", "cfdp_set_exact",
+    "cfdp_commit", "cfdp_plan", "cfdp_set_int_exchange", "cfdp_get_peer_plan", "cfdp_get_exchange_entry", "cfdp_get_tile_exports", "cfdp_get_row_owner", "cfdp_var_to_device", "cfdp_grad_to_host", "cfdp_set_resident", "cfdp_set_exact", "cfdp_set_kernel", "cfdp_get_phase_profile",
     "cfdp_iterate", "cfdp_step_e2e", "cfdp_device_synchronize", "cfdp_finalize", "cfdp_get_stats",
     "cfdp_get_schedule", "cfdp_get_tile", "cfdp_get_tile_blob", "cfdp_get_pack_list", "cfdp_get_unpack_list", "cfdp_get_sendbuf",
     "cfdp_mesh_num_domains", "cfdp_mesh_count_faces_global", "cfdp_mesh_gen_domain",
@@ -191,6 +191,8 @@ def load() -> C.CDLL:
     sig("cfdp_grad_to_host", None, sd_p)
     sig("cfdp_set_resident", None, C.c_int)
     sig("cfdp_set_exact", None, C.c_int)
+    sig("cfdp_set_kernel", C.c_int, C.c_int, C.c_int, C.c_int)
+    sig("cfdp_get_phase_profile", C.c_int, P(C.c_ulonglong), C.c_int)
     sig("cfdp_iterate", C.c_double, C.c_int, C.c_int, C.c_int)
     sig("cfdp_step_e2e", C.c_double, C.c_int)
     sig("cfdp_device_synchronize", None)

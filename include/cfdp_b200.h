@@ -198,6 +198,14 @@ void cfdp_set_resident(int resident);
 /* exact = 1 (default): separate multiply and add in the reference's single-thread summation order
  * (bit-identical to the reference run with 1 thread); exact = 0: fused multiply-add */
 void cfdp_set_exact(int exact);
+/* after cfdp_commit: which gradient kernel runs and how its grid walks the tile list.  version 2 = production
+ * (gg_tile_pipe_kernel), 1 = one tile per CTA (second, independent implementation used by the tests to cross-check),
+ * 3 = the round-1 kernel (side-by-side timing only); chunk = consecutive tiles per CTA; persistent > 0 = that many
+ * CTAs walk all tiles, interleaved.  Returns the version in effect, -1 on error.  Defaults: CFDP_KERNEL / CFDP_CHUNK /
+ * CFDP_PERSISTENT or 2 / 8 / 0. */
+int cfdp_set_kernel(int version, int chunk, int persistent);
+/* debug (CFDP_PHASE_PROF=1): SM cycles of thread 0 summed over tiles: [0] wait for data, [1] face walk, [2] rest, [4] tiles */
+int cfdp_get_phase_profile(unsigned long long *out8, int reset);
 /* run `niter` iterations of variant over ALL hosted domains, device resident; returns the
  * device time in milliseconds (CUDA events on the compute stream) */
 double cfdp_iterate(int variant, int niter, int final_last);
@@ -246,7 +254,7 @@ int cfdp_get_schedule(const solver_data *sd, cfdp_schedule_view *v);
 /* raw tile contents for tests: returns counts, fills caller buffers when non-NULL */
 int cfdp_get_tile(const solver_data *sd, int tile, int *face_ids /*[nfaces]*/, int *halo_points /*[nhalo]*/);
 /* raw tile blob (host copy, between cfdp_plan and cfdp_commit): which = 0 gradient blob, 1 pseudo-flux blob;
- * desc8 = {row0, npts, nhalo, nfaces, maxdeg, npad, blob_bytes, halo_off}; returns blob_bytes or -1.  Layout:
+ * desc8 = {row0, npts, nhalo, nfaces | zslot << 16, maxdeg, npad, blob_bytes, halo_off}; returns blob_bytes or -1.  Layout:
  * [normals nfaces*3 f64][pad16][halo device rows nhalo u32][pad16][ELL maxdeg*npad u32]; ELL entry = tile-local
  * point | ghost << 15 | face slot << 16 | (point is p1) << 31, 0xFFFFFFFF = none; local >= CFDP_HALO_BASE(npts) = halo */
 long long cfdp_get_tile_blob(const solver_data *sd, int tile, int which, unsigned *desc8, unsigned char *bytes, long long capacity);

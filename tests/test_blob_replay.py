@@ -56,6 +56,9 @@ def test_gradient_blob_replay_bit_identical(session_factory, n, p, order, hexfra
             b = S.tile_blob(d, t)
             npts, nb = b["npts"], halo_base(b["npts"])
             assert b["row0"] % 16 == 0 and b["npad"] % 32 == 0 and b["npad"] >= npts
+            # the slot the production kernel maps padding entries to: used by no entry, zero normal (TileDesc::zslot)
+            used = (b["ell"][b["ell"] != PAD] >> 16) & 0x7FFF
+            assert b["zslot"] < b["nfaces"] and b["zslot"] not in set(used.tolist()) and not b["normals"][b["zslot"]].any()
             for i in range(npts):
                 acc = np.zeros((7, 3))
                 hv = hvar[b["row0"] + i]

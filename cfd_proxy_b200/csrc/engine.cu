@@ -100,7 +100,17 @@ struct PeerPlan {
   int remote_slot = 0;
   double *peer_recvbuf = nullptr;
   unsigned long long *peer_flags = nullptr;
+  /* direct halo stores: the peer's grad array mapped into this process, and for every row of my packed send
+   * segment the row of the peer's grad it belongs to (the peer's unpack list, exchanged at setup) */
+  double *peer_grad = nullptr;
+  std::vector<uint32_t> peer_rows;
+  bool opened = false;   /* the three mappings above came from cudaIpcOpenMemHandle (not loopback aliases) */
 };
+/* slots of the arrival-counter array every rank owns (d_arrived, 256 x u64), by peer index i:
+ *   [i]        stage number of the last put into my receive window            (put + notify variants)
+ *   [64 + i]   rows peer i has stored into my ghost rows, cumulative           (direct halo stores)
+ *   [128 + i]  epoch up to which peer i has consumed the ghost rows I stored   (direct halo stores: write credit) */
+enum { FLAG_STAGE = 0, FLAG_ROWS = 64, FLAG_CREDIT = 128, MAX_PEERS = 8 };
 
 struct Engine {
   bool configured = false, planned = false, committed = false, have_device = false;
@@ -125,6 +135,9 @@ struct Engine {
   /* fused pack: per boundary tile, the rows other domains need (export lists), written by the gradient kernel itself */
   std::vector<uint32_t> h_exp_off, h_exp_src, h_exp_dst; uint32_t *d_exp_off = nullptr, *d_exp_src = nullptr, *d_exp_dst = nullptr; int fused_pack = 1;
   /* one-sided exchange: double-buffered receive window + per-peer arrival counters (exchange_data_gaspi.c:105-151) */
+  bool loopback = false;           /* test mode (CFDP_LOOPBACK=1): halo rows between domains of this GPU take the inter-GPU path, this process being its own peer */
+  bool direct_ready = false; unsigned long long direct_epoch = 0; uint32_t *d_exp_src_direct = nullptr, *d_exp_dst_direct = nullptr, *d_sig_off = nullptr, *d_sig_ent = nullptr;
+  int last_transport = 0;          /* what the last exchange used: 0 none, 1 on-device copies only, 2 NCCL send/recv, 3 IPC put + notify, 4 direct stores into peer memory */
   bool ipc_ready = false; double *d_recvwin = nullptr; unsigned long long *d_arrived = nullptr; unsigned long long ipc_stage = 0; uint32_t max_footprint = 0;
   size_t max_blob = 0; int max_nhalo = 0;
   std::vector<int *> d_rowmap;     /* per hosted domain: [nall] global device row of host point */
@@ -247,6 +260,7 @@ extern "C" int cfdp_configure(int proc_rank, int nprocs, int ndomains_total, int
   E.sopt.slack_halo = env_int("CFDP_SLACK_HALO", 0);
   E.sopt.stage_budget = env_int("CFDP_STAGE_BUDGET", 104 * 1024); /* two tiles (two CTAs or two stages) in 228 KB of shared memory per SM */
   E.exact = env_int("CFDP_EXACT", 1);
+  E.loopback = nprocs == 1 && env_int("CFDP_LOOPBACK", 0) != 0;
   E.configured = true;
   return 0;
 }
@@ -311,6 +325,13 @@ void engine_exchange_ints(const std::vector<int> &peer, const std::vector<const 
 {
   Engine &E = g_eng;
   const size_t n = peer.size();
+  if (E.nprocs == 1) { /* loopback: this process is its own peer; the i-th send pairs with the i-th receive */
+    std::vector<size_t> si, ri;
+    for (size_t i = 0; i < n; i++) { ASSERT(peer[i] == E.proc_rank); if (scount[i]) si.push_back(i); if (rcount[i]) ri.push_back(i); }
+    ASSERT(si.size() == ri.size());
+    for (size_t j = 0; j < si.size(); j++) { ASSERT(scount[si[j]] == rcount[ri[j]]); memcpy(rbuf[ri[j]], sbuf[si[j]], (size_t)scount[si[j]] * sizeof(int)); }
+    return;
+  }
   if (g_int_exchange) {
     std::vector<const int *> sb(sbuf); std::vector<int *> rb(rbuf);
     g_int_exchange((int)n, peer.data(), sb.data(), scount.data(), rb.data(), rcount.data());
@@ -405,7 +426,7 @@ static void launch_halo_pack_domain(const Domain *d, cudaStream_t st)
   launch_halo_pack(d->tile0_i, d->sch.ntiles - d->sch.nboundary, st);
 }
 
-static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st, int nsignal = 0, bool exports = false)
+static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st, int nsignal = 0, bool exports = false, bool direct = false)
 {
   Engine &E = g_eng;
   if (ntiles <= 0) return;
@@ -414,8 +435,9 @@ static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st, 
     P.nsignal = nsignal; P.progress = E.d_progress;
     P.tile_base = (int)tile0;
     P.nexport = (exports && E.fused_pack) ? (int)E.nbtiles : 0;
-    P.exp_off = E.d_exp_off; P.exp_src = E.d_exp_src; P.exp_dst = E.d_exp_dst;
+    P.exp_off = E.d_exp_off; P.exp_src = direct ? E.d_exp_src_direct : E.d_exp_src; P.exp_dst = direct ? E.d_exp_dst_direct : E.d_exp_dst;
     P.exp_base[0] = E.d_grad; P.exp_base[1] = E.d_sendbuf;
+    P.sig_off = direct ? E.d_sig_off : nullptr; P.sig_ent = E.d_sig_ent;
     unsigned grid;
     if (E.persistent > 0) { /* interleaved: CTA b walks tiles b, b + grid, ...: the tiles in flight at any time are neighbours in the tile order */
       grid = (unsigned)std::min<long long>(ntiles, (long long)E.persistent);
@@ -607,12 +629,12 @@ extern "C" void cfdp_plan(void)
     if (a->ndomains == 1) continue;
     for (int sl = 0; sl < a->ncommdomains; sl++) {
       const int k = a->commpartner[sl];
-      if (engine_domain_by_id(k)) { /* ghost rows of a owned by k, both on this GPU: one device copy */
+      if (engine_domain_by_id(k) && !E.loopback) { /* ghost rows of a owned by k, both on this GPU: one device copy */
         const std::vector<uint32_t> &dst = E.recv_rows_of[{a->iProc, k}], &src = E.send_rows_of[{k, a->iProc}];
         ASSERT(dst.size() == src.size());
         E.h_loc_dst.insert(E.h_loc_dst.end(), dst.begin(), dst.end()); E.h_loc_src.insert(E.h_loc_src.end(), src.begin(), src.end());
       } else {
-        const int q = engine_proc_of_domain(k);
+        const int q = engine_proc_of_domain(k); /* loopback: q is this process */
         if (a->sendcount[k]) send_segs[q].push_back({a->iProc, k, &E.send_rows_of[{a->iProc, k}]});
         if (a->recvcount[k]) recv_segs[q].push_back({k, a->iProc, &E.recv_rows_of[{a->iProc, k}]});
       }
@@ -635,6 +657,7 @@ extern "C" void cfdp_plan(void)
     E.peers.push_back(pp);
   }
   E.n_send = (long long)E.h_send_rows.size(); E.n_recv = (long long)E.h_recv_rows.size();
+  ASSERT(E.peers.size() <= (size_t)MAX_PEERS);
 
   /* 4. export lists (fused pack, threads.c:187-249 "pack while computing"): for every boundary tile the rows of it
    * that some other domain needs, with their destination: a ghost row of a domain hosted on this GPU (bit 31
@@ -715,6 +738,8 @@ extern "C" int cfdp_set_kernel(int version, int chunk, int persistent)
 }
 
 static void ipc_setup(void);
+typedef CUresult (*wait_value64_fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+static wait_value64_fn get_wait_value64(void);
 
 /* device part: allocate, upload, configure the kernel */
 extern "C" void cfdp_commit(void)
@@ -871,6 +896,35 @@ __global__ void notify_kernel(unsigned long long *flag, unsigned long long value
   __threadfence_system();
 }
 
+/* exchange one int with EVERY other process and AND the results: all ranks must agree on the transport, or one side
+ * would wait on a flag while the other sits in an NCCL group */
+static bool all_procs_agree(bool mine)
+{
+  Engine &E = g_eng;
+  if (E.nprocs == 1) return mine;
+  const int n = E.nprocs - 1;
+  std::vector<int> sv((size_t)n, mine ? 1 : 0), rv((size_t)n, 0);
+  std::vector<int> peer; std::vector<const int *> sp; std::vector<int> sc; std::vector<int *> rp; std::vector<int> rc;
+  for (int q = 0, k = 0; q < E.nprocs; q++) if (q != E.proc_rank) { peer.push_back(q); sp.push_back(&sv[(size_t)k]); sc.push_back(1); rp.push_back(nullptr); rc.push_back(0); k++; }
+  for (int q = 0, k = 0; q < E.nprocs; q++) if (q != E.proc_rank) { peer.push_back(q); sp.push_back(nullptr); sc.push_back(0); rp.push_back(&rv[(size_t)k]); rc.push_back(1); k++; }
+  engine_exchange_ints(peer, sp, sc, rp, rc);
+  bool all = mine;
+  for (int v : rv) all = all && v != 0;
+  return all;
+}
+
+static void ipc_close_peers(void)
+{
+  for (PeerPlan &p : g_eng.peers) {
+    if (p.opened) {
+      if (p.peer_recvbuf) cudaIpcCloseMemHandle(p.peer_recvbuf);
+      if (p.peer_flags) cudaIpcCloseMemHandle(p.peer_flags);
+      if (p.peer_grad) cudaIpcCloseMemHandle(p.peer_grad);
+    }
+    p.peer_recvbuf = nullptr; p.peer_flags = nullptr; p.peer_grad = nullptr; p.opened = false;
+  }
+}
+
 static void ipc_setup(void)
 {
   Engine &E = g_eng;
@@ -879,41 +933,96 @@ static void ipc_setup(void)
   CUDA_CHECK(cudaMalloc(&E.d_recvwin, (size_t)std::max<long long>(E.n_recv, 1) * 2 * CFDP_DIM2 * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&E.d_arrived, 256 * sizeof(unsigned long long)));
   CUDA_CHECK(cudaMemset(E.d_arrived, 0, 256 * sizeof(unsigned long long)));
-  ASSERT(np <= 256);
-  cudaIpcMemHandle_t hwin, hflag;
-  CUDA_CHECK(cudaIpcGetMemHandle(&hwin, E.d_recvwin));
-  CUDA_CHECK(cudaIpcGetMemHandle(&hflag, E.d_arrived));
+  /* 1. handles of my receive window, counters and grad array + where each peer's rows go + my unpack rows for that
+   * peer (they become the destinations of the peer's direct stores) */
+  cudaIpcMemHandle_t hwin, hflag, hgrad;
+  memset(&hwin, 0, sizeof hwin); memset(&hflag, 0, sizeof hflag); memset(&hgrad, 0, sizeof hgrad);
+  if (!E.loopback) {
+    CUDA_CHECK(cudaIpcGetMemHandle(&hwin, E.d_recvwin));
+    CUDA_CHECK(cudaIpcGetMemHandle(&hflag, E.d_arrived));
+    CUDA_CHECK(cudaIpcGetMemHandle(&hgrad, E.d_grad));
+  }
   const int HW = (int)(sizeof(cudaIpcMemHandle_t) / sizeof(int)); /* 16 */
-  const int MSG = 2 * HW + 5;
-  std::vector<std::vector<int>> sb(np, std::vector<int>((size_t)MSG)), rb(np, std::vector<int>((size_t)MSG));
+  const int HDR = 3 * HW + 5;
+  std::vector<std::vector<int>> sb(np), rb(np);
   std::vector<int> peer; std::vector<const int *> sp; std::vector<int> sc; std::vector<int *> rp; std::vector<int> rc;
   for (size_t i = 0; i < np; i++) {
-    memcpy(sb[i].data(), &hwin, sizeof hwin); memcpy(sb[i].data() + HW, &hflag, sizeof hflag);
-    sb[i][2 * HW + 0] = (int)(E.peers[i].recv_off & 0x7FFFFFFF); sb[i][2 * HW + 1] = (int)(E.peers[i].recv_off >> 31);
-    sb[i][2 * HW + 2] = (int)i;                                   /* the counter this peer bumps */
-    sb[i][2 * HW + 3] = (int)(E.n_recv & 0x7FFFFFFF); sb[i][2 * HW + 4] = (int)(E.n_recv >> 31);
-    peer.push_back(E.peers[i].proc); sp.push_back(sb[i].data()); sc.push_back(MSG); rp.push_back(nullptr); rc.push_back(0);
+    const PeerPlan &p = E.peers[i];
+    sb[i].assign((size_t)HDR + (size_t)p.recv_rows, 0);
+    memcpy(sb[i].data(), &hwin, sizeof hwin); memcpy(sb[i].data() + HW, &hflag, sizeof hflag); memcpy(sb[i].data() + 2 * HW, &hgrad, sizeof hgrad);
+    sb[i][3 * HW + 0] = (int)(p.recv_off & 0x7FFFFFFF); sb[i][3 * HW + 1] = (int)(p.recv_off >> 31);
+    sb[i][3 * HW + 2] = (int)i;                                   /* the counters this peer bumps */
+    sb[i][3 * HW + 3] = (int)(E.n_recv & 0x7FFFFFFF); sb[i][3 * HW + 4] = (int)(E.n_recv >> 31);
+    for (long long j = 0; j < p.recv_rows; j++) sb[i][(size_t)HDR + (size_t)j] = (int)E.h_recv_rows[(size_t)(p.recv_off + j)];
+    rb[i].assign((size_t)HDR + (size_t)p.send_rows, 0);           /* the peer receives what I send */
+    peer.push_back(p.proc); sp.push_back(sb[i].data()); sc.push_back((int)sb[i].size()); rp.push_back(nullptr); rc.push_back(0);
   }
-  for (size_t i = 0; i < np; i++) { peer.push_back(E.peers[i].proc); sp.push_back(nullptr); sc.push_back(0); rp.push_back(rb[i].data()); rc.push_back(MSG); }
+  for (size_t i = 0; i < np; i++) { peer.push_back(E.peers[i].proc); sp.push_back(nullptr); sc.push_back(0); rp.push_back(rb[i].data()); rc.push_back((int)rb[i].size()); }
   engine_exchange_ints(peer, sp, sc, rp, rc);
-  for (size_t i = 0; i < np; i++) {
+  /* 2. map the peers' buffers */
+  bool ok = get_wait_value64() != nullptr;
+  for (size_t i = 0; i < np && ok; i++) {
     PeerPlan &p = E.peers[i];
-    cudaIpcMemHandle_t h1, h2;
-    memcpy(&h1, rb[i].data(), sizeof h1); memcpy(&h2, rb[i].data() + HW, sizeof h2);
-    void *w = nullptr, *f = nullptr;
-    if (cudaIpcOpenMemHandle(&w, h1, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-        cudaIpcOpenMemHandle(&f, h2, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-      /* no peer mapping between these GPUs: the one-sided variant names keep using the NCCL transport */
-      fprintf(stderr, "cfdp: CUDA IPC mapping of rank %d's window failed (%s); one-sided variants fall back to NCCL\n",
-              p.proc, cudaGetErrorString(cudaGetLastError()));
-      return;
+    if (E.loopback) { p.peer_recvbuf = E.d_recvwin; p.peer_flags = E.d_arrived; p.peer_grad = E.d_grad; }
+    else {
+      cudaIpcMemHandle_t h1, h2, h3;
+      memcpy(&h1, rb[i].data(), sizeof h1); memcpy(&h2, rb[i].data() + HW, sizeof h2); memcpy(&h3, rb[i].data() + 2 * HW, sizeof h3);
+      void *w = nullptr, *f = nullptr, *g = nullptr;
+      p.opened = true;
+      if (cudaIpcOpenMemHandle(&w, h1, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&f, h2, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&g, h3, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        fprintf(stderr, "cfdp: rank %d cannot map the buffers of rank %d over CUDA IPC (%s)\n", E.proc_rank, p.proc, cudaGetErrorString(cudaGetLastError()));
+        ok = false;
+      }
+      p.peer_recvbuf = (double *)w; p.peer_flags = (unsigned long long *)f; p.peer_grad = (double *)g;
     }
-    p.peer_recvbuf = (double *)w; p.peer_flags = (unsigned long long *)f;
-    p.remote_recv_off = (long long)rb[i][2 * HW + 0] | ((long long)rb[i][2 * HW + 1] << 31);
-    p.remote_slot = rb[i][2 * HW + 2];
-    p.remote_recv_total = (long long)rb[i][2 * HW + 3] | ((long long)rb[i][2 * HW + 4] << 31);
+    p.remote_recv_off = (long long)rb[i][3 * HW + 0] | ((long long)rb[i][3 * HW + 1] << 31);
+    p.remote_slot = rb[i][3 * HW + 2];
+    p.remote_recv_total = (long long)rb[i][3 * HW + 3] | ((long long)rb[i][3 * HW + 4] << 31);
+    p.peer_rows.resize((size_t)p.send_rows);
+    for (long long j = 0; j < p.send_rows; j++) p.peer_rows[(size_t)j] = (uint32_t)rb[i][(size_t)HDR + (size_t)j];
+  }
+  /* 3. every rank uses the one-sided transports, or none does (a rank that fell back to NCCL alone would
+   * deadlock against peers waiting on its flags) */
+  if (!all_procs_agree(ok)) {
+    if (E.proc_rank == 0) fprintf(stderr, "cfdp: CUDA IPC peer mapping is not available on every rank: the one-sided variants (gaspi_*, mpifence_*, mpipscw_*) use the NCCL transport\n");
+    ipc_close_peers();
+    return;
   }
   E.ipc_ready = true;
+
+  /* 4. direct halo stores: the export lists once more, remote rows addressed in the peers' grad arrays
+   * (destination array 2 + peer), and per boundary tile the (peer, rows) pairs its stores complete */
+  {
+    std::vector<uint32_t> src2(E.h_exp_src), dst2(E.h_exp_dst);
+    std::vector<std::vector<uint32_t>> tile_peer_rows((size_t)E.nbtiles, std::vector<uint32_t>(np, 0));
+    for (long long t = 0; t < E.nbtiles; t++)
+      for (uint32_t e = E.h_exp_off[(size_t)t]; e < E.h_exp_off[(size_t)t + 1]; e++) {
+        if ((src2[e] >> 16) != 1u) continue;                       /* a slot of the packed send buffer ... */
+        const long long slot = (long long)dst2[e];
+        size_t pi = 0;
+        while (pi < np && !(slot >= E.peers[pi].send_off && slot < E.peers[pi].send_off + E.peers[pi].send_rows)) pi++;
+        ASSERT(pi < np);
+        dst2[e] = E.peers[pi].peer_rows[(size_t)(slot - E.peers[pi].send_off)];   /* ... becomes a ghost row of the peer */
+        src2[e] = (src2[e] & 0xFFFFu) | ((uint32_t)(2 + pi) << 16);
+        tile_peer_rows[(size_t)t][pi]++;
+      }
+    std::vector<uint32_t> sig_off((size_t)E.nbtiles + 1, 0), sig_ent;
+    for (long long t = 0; t < E.nbtiles; t++) {
+      for (size_t pi = 0; pi < np; pi++)
+        if (tile_peer_rows[(size_t)t][pi]) sig_ent.push_back((uint32_t)pi | (tile_peer_rows[(size_t)t][pi] << 4));
+      sig_off[(size_t)t + 1] = (uint32_t)sig_ent.size();
+    }
+    E.d_exp_src_direct = upload(src2); E.d_exp_dst_direct = upload(dst2);
+    E.d_sig_off = upload(sig_off); E.d_sig_ent = upload(sig_ent);
+    for (size_t pi = 0; pi < np; pi++) {
+      E.pipe.exp_base[2 + pi] = E.peers[pi].peer_grad;
+      E.pipe.sig_flag[pi] = E.peers[pi].peer_flags + FLAG_ROWS + E.peers[pi].remote_slot;
+    }
+    E.direct_ready = env_int("CFDP_DIRECT", 1) != 0;
+    E.direct_epoch = 0;
+  }
 }
 
 static CUresult stream_wait_geq(cudaStream_t st, const void *addr, unsigned long long value);
@@ -922,7 +1031,9 @@ static void enqueue_exchange_onesided(cudaStream_t st, bool packed)
 {
   Engine &E = g_eng;
   if (!packed) launch_rows_copy(E.d_grad, E.d_loc_dst, E.d_grad, E.d_loc_src, E.n_local, CFDP_DIM2, st);
+  E.last_transport = 1;
   if (E.peers.empty()) return;
+  E.last_transport = 3;
   const unsigned long long stage = E.ipc_stage++;
   const int half = (int)(stage & 1);                                                               /* exchange_data_gaspi.c:181 */
   if (!packed) launch_rows_copy(E.d_sendbuf, nullptr, E.d_grad, E.d_send_rows, E.n_send, CFDP_DIM2, st);      /* threads.c:791-813 */
@@ -931,13 +1042,13 @@ static void enqueue_exchange_onesided(cudaStream_t st, bool packed)
     double *dst = p.peer_recvbuf + ((size_t)half * (size_t)p.remote_recv_total + (size_t)p.remote_recv_off) * CFDP_DIM2;
     CUDA_CHECK(cudaMemcpyAsync(dst, E.d_sendbuf + p.send_off * CFDP_DIM2, (size_t)p.send_rows * CFDP_DIM2 * sizeof(double),
                                cudaMemcpyDeviceToDevice, st));                                      /* gaspi_write ... */
-    notify_kernel<<<1, 1, 0, st>>>(p.peer_flags + p.remote_slot, stage + 1);                        /* ... _notify */
+    notify_kernel<<<1, 1, 0, st>>>(p.peer_flags + FLAG_STAGE + p.remote_slot, stage + 1);           /* ... _notify */
     CUDA_CHECK(cudaGetLastError());
     E.launches++;
   }
   for (size_t i = 0; i < E.peers.size(); i++) {                                                     /* gaspi_notify_waitsome, exchange_data_gaspi.c:252-262 */
     if (!E.peers[i].recv_rows) continue;
-    CUresult r = stream_wait_geq(st, E.d_arrived + i, stage + 1);
+    CUresult r = stream_wait_geq(st, E.d_arrived + FLAG_STAGE + i, stage + 1);
     ASSERT(r == CUDA_SUCCESS);
   }
   launch_rows_copy(E.d_grad, E.d_recv_rows, E.d_recvwin + (size_t)half * (size_t)E.n_recv * CFDP_DIM2, nullptr, E.n_recv, CFDP_DIM2, st);
@@ -948,8 +1059,16 @@ static void enqueue_exchange(cudaStream_t st, bool packed)
   Engine &E = g_eng;
   /* halo rows whose owner lives on this GPU: one gather/scatter, no staging */
   if (!packed) launch_rows_copy(E.d_grad, E.d_loc_dst, E.d_grad, E.d_loc_src, E.n_local, CFDP_DIM2, st);
+  E.last_transport = 1;
   if (E.peers.empty()) return;
+  E.last_transport = 2;
   if (!packed) launch_rows_copy(E.d_sendbuf, nullptr, E.d_grad, E.d_send_rows, E.n_send, CFDP_DIM2, st);      /* threads.c:791-813 */
+  if (E.loopback) { /* test mode: this process is its own peer, the message is one device copy */
+    ASSERT(E.n_send == E.n_recv);
+    CUDA_CHECK(cudaMemcpyAsync(E.d_recvbuf, E.d_sendbuf, (size_t)E.n_send * CFDP_DIM2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    launch_rows_copy(E.d_grad, E.d_recv_rows, E.d_recvbuf, nullptr, E.n_recv, CFDP_DIM2, st);
+    return;
+  }
   NCCL_CHECK(g_nccl.GroupStart());
   for (const PeerPlan &p : E.peers) {                                                               /* exchange_data_mpi.c:96-166 */
     if (p.recv_rows) NCCL_CHECK(g_nccl.Recv(E.d_recvbuf + p.recv_off * CFDP_DIM2, (size_t)p.recv_rows * CFDP_DIM2, NCCL_FLOAT64, p.proc, E.comm, st));
@@ -959,7 +1078,6 @@ static void enqueue_exchange(cudaStream_t st, bool packed)
   launch_rows_copy(E.d_grad, E.d_recv_rows, E.d_recvbuf, nullptr, E.n_recv, CFDP_DIM2, st);      /* threads.c:816-839 */
 }
 
-typedef CUresult (*wait_value64_fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
 static wait_value64_fn get_wait_value64(void)
 {
   static wait_value64_fn fn = nullptr;
@@ -990,10 +1108,55 @@ static void enqueue_exchange_for(int variant, cudaStream_t st, bool packed)
 }
 static bool kernel_packs(void) { return g_eng.fused_pack && g_eng.kernel_version == 2; }
 
+/* ------------------------------------------------------------------------------------------
+ * Direct halo stores (the *_async one-sided variants): the boundary tiles of the gradient kernel store the rows a
+ * peer GPU needs straight into the ghost rows of the peer's grad array (CUDA IPC mapping, NVLink) and add the number
+ * of rows to the peer's arrival counter (red.release.sys) -- per partner, the moment a tile's send points are final
+ * (threads.c:268-306, exchange_data_gaspi.c:105-151).  No pack, no transfer, no unpack kernel.  A rank's iteration
+ * is complete when every peer's counter has reached epoch * rows (stream wait, no kernel spins).  Before a rank
+ * overwrites the ghost rows of a peer in the next epoch it needs that peer's credit: "every consumer of the previous
+ * rows that was enqueued before my next iteration has finished" (the analogue of the reference's double-buffered
+ * segments + queue back-pressure, exchange_data_gaspi.c:181,230, queue.c:20-33).
+ * ---------------------------------------------------------------------------------------- */
+struct CreditArgs { unsigned long long *flag[MAX_PEERS]; int n; };
+__global__ void credit_kernel(CreditArgs a, unsigned long long value)
+{
+  const int i = threadIdx.x;
+  if (i < a.n) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(a.flag[i]) = value;
+    __threadfence_system();
+  }
+}
+
+static bool use_direct(int variant) { return variant == CFDP_GASPI_ASYNC && g_eng.direct_ready && kernel_packs() && !g_eng.peers.empty(); }
+
+static void run_iteration_direct(void)
+{
+  Engine &E = g_eng;
+  const unsigned long long e = ++E.direct_epoch;
+  if (e > 1) {
+    CreditArgs ca; ca.n = 0;
+    for (const PeerPlan &p : E.peers) if (p.recv_rows) ca.flag[ca.n++] = p.peer_flags + FLAG_CREDIT + p.remote_slot;
+    if (ca.n) { credit_kernel<<<1, 32, 0, E.s_comp>>>(ca, e - 1); CUDA_CHECK(cudaGetLastError()); E.launches++; }
+    for (size_t i = 0; i < E.peers.size(); i++)
+      if (E.peers[i].send_rows) { CUresult r = stream_wait_geq(E.s_comp, E.d_arrived + FLAG_CREDIT + i, e - 1); ASSERT(r == CUDA_SUCCESS); }
+  }
+  launch_gradient(0, E.ntiles, E.s_comp, 0, true, true);
+  if (E.timeline_ek) CUDA_CHECK(cudaEventRecord(E.timeline_ek, E.s_comp));
+  for (size_t i = 0; i < E.peers.size(); i++)
+    if (E.peers[i].recv_rows) { CUresult r = stream_wait_geq(E.s_comp, E.d_arrived + FLAG_ROWS + i, e * (unsigned long long)E.peers[i].recv_rows); ASSERT(r == CUDA_SUCCESS); }
+  if (E.timeline_ex) CUDA_CHECK(cudaEventRecord(E.timeline_ex, E.s_comp));
+  E.last_transport = 4;
+  for (Domain *d : E.doms)
+    if (d->cd->ndomains > 1) { d->cd->send_stage++; d->cd->recv_stage++; d->cd->comm_stage++; }
+}
+
 static void run_iteration(int variant)
 {
   Engine &E = g_eng;
   const bool overlap = (variant == CFDP_MPI_ASYNC || variant == CFDP_GASPI_ASYNC);
+  if (variant != CFDP_COMM_FREE && use_direct(variant)) { run_iteration_direct(); return; }
   if (variant == CFDP_COMM_FREE || !have_exchange()) {
     launch_gradient(0, E.ntiles, E.s_comp);                       /* gradients.c:150-165 */
   } else if (!overlap) {
@@ -1308,6 +1471,8 @@ extern "C" void cfdp_get_stats(cfdp_stats *st)
   st->alg_bytes = E.alg_bytes; st->h2d_bytes = E.nall * NGRAD * 8; st->d2h_bytes = E.nall * CFDP_DIM2 * 8;
   for (Domain *d : E.doms) { st->lds_wavefronts_min += d->sch.lds_wavefronts_min; st->lds_wavefronts_est += d->sch.lds_wavefronts_est; }
   st->launches = E.launches; st->last_kernel_ms = E.last_kernel_ms; st->smem_bytes = E.smem_bytes;
+  st->halo_pack_bytes = E.halo_rows * NGRAD * 8; st->transport = E.last_transport; st->ipc_ready = E.ipc_ready ? 1 : 0; st->direct_ready = E.direct_ready ? 1 : 0; st->loopback = E.loopback ? 1 : 0;
+  st->device_bytes = (long long)E.blob_bytes + (long long)E.fblob_bytes + E.rows * (NGRAD + CFDP_DIM2 + 1) * 8 + E.halo_rows * NGRAD * 8 + (long long)E.stage_bytes + (E.d_flux ? E.rows * NFLUX * 8 : 0) + (E.n_send + E.n_recv * 3) * CFDP_DIM2 * 8;
   st->flux_alg_bytes = E.flux_alg_bytes; st->last_flux_ms = E.last_flux_ms; st->flux_smem_bytes = (int)E.flux_smem; st->flux_blob_bytes = (long long)E.fblob_bytes;
 }
 
@@ -1452,10 +1617,10 @@ extern "C" void cfdp_finalize(void)
     cudaFree(E.d_loc_dst); cudaFree(E.d_loc_src); cudaFree(E.d_exp_off); cudaFree(E.d_exp_src); cudaFree(E.d_exp_dst); cudaFree(E.d_send_rows); cudaFree(E.d_recv_rows); cudaFree(E.d_sendbuf); cudaFree(E.d_recvbuf);
     for (int *p : E.d_rowmap) cudaFree(p);
   }
-  if (E.ipc_ready) {
-    for (PeerPlan &p : E.peers) { if (p.peer_recvbuf) cudaIpcCloseMemHandle(p.peer_recvbuf); if (p.peer_flags) cudaIpcCloseMemHandle(p.peer_flags); }
-    cudaFree(E.d_recvwin); cudaFree(E.d_arrived); E.d_recvwin = nullptr; E.d_arrived = nullptr; E.ipc_ready = false; E.ipc_stage = 0;
-  }
+  ipc_close_peers();
+  cudaFree(E.d_recvwin); cudaFree(E.d_arrived); E.d_recvwin = nullptr; E.d_arrived = nullptr; E.ipc_ready = false; E.ipc_stage = 0;
+  cudaFree(E.d_exp_src_direct); cudaFree(E.d_exp_dst_direct); cudaFree(E.d_sig_off); cudaFree(E.d_sig_ent);
+  E.d_exp_src_direct = E.d_exp_dst_direct = E.d_sig_off = E.d_sig_ent = nullptr; E.direct_ready = false; E.direct_epoch = 0; E.last_transport = 0;
   for (Domain *d : E.doms) {
     /* host containers this library allocated (read_solver_data / read_communication_data / cfdp_attach_mesh) */
     if (d->sd) {

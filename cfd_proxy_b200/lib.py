@@ -90,7 +90,12 @@ class Stats(C.Structure):
         ("nprocs", C.c_int), ("proc_rank", C.c_int), ("ndomains_hosted", C.c_int),
         ("tile_points", C.c_int), ("smem_bytes", C.c_int), ("flux_smem_bytes", C.c_int),
         ("flux_alg_bytes", C.c_longlong), ("last_flux_ms", C.c_double), ("flux_blob_bytes", C.c_longlong),
+        ("halo_pack_bytes", C.c_longlong), ("device_bytes", C.c_longlong),
+        ("transport", C.c_int), ("ipc_ready", C.c_int), ("direct_ready", C.c_int), ("loopback", C.c_int),
     ]
+
+
+TRANSPORTS = {0: "none", 1: "on-device copies", 2: "nccl send/recv", 3: "cuda-ipc put+notify", 4: "direct stores into peer memory (cuda-ipc mapping, nvlink)"}
 
 
 class ScheduleView(C.Structure):

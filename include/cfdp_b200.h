@@ -237,6 +237,10 @@ typedef struct {
   long long flux_alg_bytes;  /* algorithmic bytes of one pseudo-flux pass: 32 B per face + 72 B per point + 24 B per own point */
   double last_flux_ms;       /* mean device time of one pseudo-flux pass in the last cfdp_flux_iterate */
   long long flux_blob_bytes; /* size of the pseudo-flux tile blobs (0: the kernel reads the gradient blobs) */
+  long long halo_pack_bytes; /* packed halo rows (one contiguous block per tile, refreshed at every upload of var): bytes the gradient kernel reads on top of the algorithmic ones */
+  long long device_bytes;    /* device memory this library holds */
+  int transport;             /* what the last exchange used: 0 none, 1 on-device copies only, 2 NCCL send/recv, 3 CUDA-IPC put + notify, 4 direct stores into peer memory */
+  int ipc_ready, direct_ready, loopback;
 } cfdp_stats;
 void cfdp_get_stats(cfdp_stats *st);
 

@@ -30,6 +30,7 @@ def main():
     S.load_spec(spec)
     S.setup()
     errors = []
+    transports = {}
     for variant in ("mpi_bulk_sync", "mpi_early_recv", "mpi_async", "gaspi_bulk_sync", "gaspi_async"):  # gaspi_* = CUDA-IPC put + notify
         for d in S.domains:
             d.grad[:] = np.nan
@@ -37,6 +38,7 @@ def main():
         S.lib.cfdp_set_resident(1)
         S.set_flux(True)                 # every iteration: gradient + exchange, then the pseudo flux on the exchanged rows
         S.iterate(variant, 3)
+        transports[variant] = int(S.stats().transport)
         S.download_grad()
         S.download_flux()
         for d in S.domains:
@@ -48,7 +50,10 @@ def main():
             if bad:
                 errors.append(f"{variant}: domain {d.rank}: {bad} pseudo-flux words differ")
     st = S.stats()
-    out = dict(rank=S.proc_rank, errors=errors, local=int(st.send_rows_local), remote=int(st.send_rows_remote))
+    want_t = dict(mpi_bulk_sync=2, mpi_early_recv=2, mpi_async=2, gaspi_bulk_sync=3 if st.ipc_ready else 2, gaspi_async=4 if st.direct_ready else (3 if st.ipc_ready else 2))
+    if st.send_rows_remote and transports != want_t:
+        errors.append(f"transports {transports} != {want_t}")
+    out = dict(rank=S.proc_rank, errors=errors, transports=transports, local=int(st.send_rows_local), remote=int(st.send_rows_remote))
     with open(os.path.join(os.environ["CFDP_MP_OUT"], f"rank{S.proc_rank}.json"), "w") as f:
         json.dump(out, f)
     S.close()

@@ -41,7 +41,7 @@ def main():
             for rnd in range(rounds):     # configurations interleaved: drift hits all of them alike
                 for kc in res:
                     ver, chunk, pers, order = (int(x) for x in (kc.split(".") + ["0"])[:4])
-                    os.environ["CFDP_ORDER"] = str(order)
+                    os.environ["CFDP_VARIANT"] = str(order)
                     assert S.lib.cfdp_set_kernel(ver, chunk, pers) == ver
                     S.iterate("comm_free", 2)
                     res[kc]["k"].append(S.iterate("comm_free", iters) / iters)
@@ -52,7 +52,7 @@ def main():
                 prof = None
                 if os.environ.get("CFDP_PHASE_PROF"):
                     ver, chunk, pers, order = (int(x) for x in (kc.split(".") + ["0"])[:4])
-                    os.environ["CFDP_ORDER"] = str(order)
+                    os.environ["CFDP_VARIANT"] = str(order)
                     S.lib.cfdp_set_kernel(ver, chunk, pers)
                     buf = (C.c_ulonglong * 8)()
                     S.lib.cfdp_get_phase_profile(buf, 1)

@@ -44,6 +44,58 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def kernel_src_sha():
+    """Hash of the sources the gradient kernel and its schedule are built from: an ncu traffic capture is only quoted
+    for the build it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("gg_kernels.cuh", "engine.cu", "schedule.cpp", "common.h"):
+        with open(os.path.join(ROOT, "cfd_proxy_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def parity_leg(world, rank, variants):
+    """Outside every timed region: a small mesh with the SAME process / GPU topology as the benchmark (8 domains, 8/N per
+    GPU), every exchange variant, all own AND ghost rows of the hosted domains bit-compared with the oracle
+    (oracle/gg_oracle.c: test infrastructure, used here as the checker only).  Mirrors the reference's in-line
+    checks of its exchange (exchange_data_mpi.c:189, thread_comm.c:159-205)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import cfd_proxy_b200.mesh as M
+    from cfd_proxy_b200 import lib as L
+    from cfd_proxy_b200.driver import session_from_env
+    from oracle import oracle as O
+    spec = M.make_spec((48, 40, 32), (2, 2, 2), order="lex", jitter=0.1, hexfrac=0.25)
+    doms = [M.gen_domain(spec, r) for r in range(8)]
+    recv, send = O.recvsend_index(doms)
+    want = [O.gradients(d, M.var_for(d), is_send=O.is_send_mask(d, send[a]), order=1) for a, d in enumerate(doms)]
+    want = O.exchange(want, recv, send)
+    S = session_from_env(8)
+    S.load_spec(spec)
+    S.setup()
+    S.lib.cfdp_set_resident(1)
+    bad, words, transports = 0, 0, {}
+    for v in variants:
+        for d in S.domains:
+            d.grad[:] = np.nan
+        S.upload_grad()
+        S.iterate(v, 3)
+        transports[v] = L.TRANSPORTS[int(S.stats().transport)]
+        S.download_grad()
+        for d in S.domains:
+            bad += int((d.grad.view(np.uint64) != want[d.rank].view(np.uint64)).sum())
+            words += d.grad.size
+    S.close()
+    if world > 1:
+        t = torch.tensor([bad, words], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        bad, words = int(t[0].item()), int(t[1].item())
+    return dict(ok=bad == 0, words=words, mismatches=bad, variants=list(variants), transport=transports,
+                mesh="48x40x32 lattice, 8 domains, %d per GPU, 3 iterations per variant, own + ghost rows vs oracle/gg_oracle.c (bit-exact)" % (8 // world))
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -101,45 +153,53 @@ class ClockSampler:
 # reference arm / cpu baseline: the unmodified reference (oracle/_ref) on the host cores
 # ----------------------------------------------------------------------------------------------
 def run_reference_sample(steps, warmup, mpoints=2.0, variant="mpi_async", with_flux=False):
-    """Times the reference's own CPU implementation (oracle/_ref/ref_harness: unmodified
-    gradients.c / exchange_data_mpi.c over the shm-MPI shim) on a bounded sample of the workload:
-    same mesh family and 8-domain partition, `mpoints` million points.  Falls back to the C
-    restatement (oracle/gg_oracle.c, 1 thread) when oracle/_ref is absent."""
-    import numpy as np
-    import cfd_proxy_b200.mesh as M
+    """Times the reference's own CPU implementation (oracle/_ref/ref_harness: unmodified gradients.c /
+    exchange_data_mpi.c over the shm-MPI shim, 8 ranks x cores/8 OpenMP threads) on the same mesh family and 8-domain
+    partition with `mpoints` million points: `warmup` untimed repeat(s) of `steps` iterations, then one timed repeat
+    (the harness reports the best repeat).  The mesh files come from the standalone oracle/_ref/mesh_tool: this
+    process and its children never load libcfdp_b200.so.  Falls back to the C restatement (oracle/gg_oracle.c,
+    1 thread) when oracle/_ref is absent."""
     from oracle import oracle as O
     ncores = os.cpu_count() or 1
     n = lattice_for(mpoints)
-    spec = M.make_spec(n, (2, 2, 2), order="lex", jitter=0.1)
     tmp = tempfile.mkdtemp(prefix="cfdp_ref_")
     prefix = os.path.join(tmp, "synth")
-    if O.have_ref():
-        doms = M.write_mesh(prefix, spec, lvl=1)
-        faces = int(sum(int(((d["fpoint"][:, 0] < d["nown"]) | (d["fpoint"][:, 1] < d["nown"])).sum()) for d in doms))
-        threads = max(1, ncores // 8)
-        res = O.run_ref(prefix, 1, 8, variant, steps, os.path.join(tmp, "out"), threads=threads, repeats=max(2, 1 + (1 if warmup else 0)),
-                        timeout=1500, with_flux=with_flux)
-        best = max(r["time"]["best_s"] for r in res)   # slowest rank of the best repeat
-        kind, cores = "reference", min(ncores, 8 * threads)
-        sample = (f"{n[0]}x{n[1]}x{n[2]} lattice ({sum(d['nown'] for d in doms)/1e6:.2f} M points, {faces/1e6:.2f} M faces), 8 ranks x "
-                  f"{threads} OpenMP threads over the shm-MPI shim, variant {variant}, {steps} iterations, best of "
-                  f"{max(2, 1 + (1 if warmup else 0))} repeats (first repeat is the warm-up)")
-    else:
-        doms = [M.gen_domain(spec, r) for r in range(8)]
-        recv, send = O.recvsend_index(doms)
-        faces = int(sum(int(((d["fpoint"][:, 0] < d["nown"]) | (d["fpoint"][:, 1] < d["nown"])).sum()) for d in doms))
-        vars_ = [M.var_for(d) for d in doms]
-        best = 1e300
-        for rep in range(2):
-            t = time.perf_counter()
-            for _ in range(steps):
-                g = [O.gradients(d, v, is_send=O.is_send_mask(d, send[a])) for a, (d, v) in enumerate(zip(doms, vars_))]
-                O.exchange(g, recv, send)
-            best = min(best, time.perf_counter() - t)
-        kind, cores = "port", 1
-        sample = f"{n[0]}x{n[1]}x{n[2]} lattice, 8 domains serially, oracle/gg_oracle.c, {steps} iterations"
-    import shutil
-    shutil.rmtree(tmp, ignore_errors=True)
+    try:
+        if O.have_ref() and os.path.exists(os.path.join(O.REF_DIR, "mesh_tool")):
+            r = subprocess.run([os.path.join(O.REF_DIR, "mesh_tool"), prefix, "1", str(n[0]), str(n[1]), str(n[2]), "2", "2", "2", "0", "8", "0", "0.1", "0x5DEECE66D"],
+                               capture_output=True, text=True, timeout=1500)
+            if r.returncode != 0:
+                raise RuntimeError("mesh_tool failed: " + r.stderr[-500:])
+            info = json.loads(r.stdout.strip().splitlines()[-1])
+            faces, points = int(info["faces"]), int(info["points"])
+            threads = max(1, ncores // 8)
+            repeats = 1 + (1 if warmup else 0)
+            res = O.run_ref(prefix, 1, 8, variant, steps, os.path.join(tmp, "out"), threads=threads, repeats=repeats,
+                            timeout=3000, with_flux=with_flux, timing_only=True)
+            best = max(r["time"]["best_s"] for r in res)   # slowest rank of the best repeat
+            kind, cores = "reference", min(ncores, 8 * threads)
+            sample = (f"{n[0]}x{n[1]}x{n[2]} lattice ({points/1e6:.2f} M points, {faces/1e6:.2f} M faces), 8 ranks x "
+                      f"{threads} OpenMP threads over the shm-MPI shim, variant {variant}, {steps} iterations per repeat, best of "
+                      f"{repeats} repeats (the first one is the warm-up)")
+        else:
+            import cfd_proxy_b200.mesh as M
+            spec = M.make_spec(n, (2, 2, 2), order="lex", jitter=0.1)
+            doms = [M.gen_domain(spec, r) for r in range(8)]
+            recv, send = O.recvsend_index(doms)
+            faces = int(sum(int(((d["fpoint"][:, 0] < d["nown"]) | (d["fpoint"][:, 1] < d["nown"])).sum()) for d in doms))
+            vars_ = [M.var_for(d) for d in doms]
+            best = 1e300
+            for rep in range(2):
+                t = time.perf_counter()
+                for _ in range(steps):
+                    g = [O.gradients(d, v, is_send=O.is_send_mask(d, send[a])) for a, (d, v) in enumerate(zip(doms, vars_))]
+                    O.exchange(g, recv, send)
+                best = min(best, time.perf_counter() - t)
+            kind, cores = "port", 1
+            sample = f"{n[0]}x{n[1]}x{n[2]} lattice, 8 domains serially, oracle/gg_oracle.c, {steps} iterations"
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
     return dict(value=faces * steps / best, unit=UNIT, cores=cores, kind=kind, sample=sample), best / steps * 1e3, faces
 
 
@@ -151,31 +211,39 @@ def main():
     ap.add_argument("--impl", default="cfdp", choices=["cfdp", "reference"])
     ap.add_argument("--mpoints", type=float, default=float(os.environ.get("CFDP_BENCH_MPOINTS", "64")),
                     help="million mesh points (default 64: BASELINE config 4 size, partitioned like config 5)")
-    ap.add_argument("--variant", default="mpi_async")
+    ap.add_argument("--variant", default=None, help="default: gaspi_async on several GPUs (direct stores into peer memory), mpi_async on one")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="length of the sustained timing loops (steady-state clocks)")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--order", default="lex", choices=["lex", "brick", "shuffle"])
     ap.add_argument("--tile-points", type=int, default=None)
     ap.add_argument("--fma", action="store_true", help="fused multiply-add instead of the reference's mul+add (not bit-exact)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-flux", action="store_true", help="skip the pseudo-flux measurements")
-    ap.add_argument("--cpu-mpoints", type=float, default=2.0)
+    ap.add_argument("--cpu-mpoints", type=float, default=None,
+                    help="mesh size of the CPU runs; default: --impl reference = the benchmark's own size (same config), in-bench cpu_baseline = a 2 M-point sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.variant is None:
+        args.variant = "gaspi_async" if world > 1 else "mpi_async"
+    bulk_variant = "gaspi_bulk_sync" if args.variant.startswith("gaspi") else "mpi_bulk_sync"
 
     n = lattice_for(args.mpoints)
-    workload = (f"synthetic tet-dual box {n[0]}x{n[1]}x{n[2]} ({n[0]*n[1]*n[2]/1e6:.1f} M points), 8 domains (2x2x2), "
-                f"{8 // max(world, 1)} domains per GPU, variant {args.variant}")
+    workload = f"synthetic tet-dual box {n[0]}x{n[1]}x{n[2]} ({n[0]*n[1]*n[2]/1e6:.1f} M points), 8 domains (2x2x2), grad + halo exchange per iteration"
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cpu, ms_step, faces = run_reference_sample(args.steps, args.warmup, mpoints=args.cpu_mpoints, variant=args.variant)
+        ref_variant = args.variant if args.variant.startswith("mpi") else "mpi_async"   # the reference build has no GASPI (BASELINE config 1: USE_GASPI off)
+        cpu_mp = args.cpu_mpoints if args.cpu_mpoints else args.mpoints
+        cpu, ms_step, faces = run_reference_sample(args.steps, args.warmup, mpoints=cpu_mp, variant=ref_variant)
         line = dict(metric=METRIC, value=cpu["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
                     data="synthetic", impl="reference",
-                    config=dict(workload=workload, sample=cpu["sample"]),
+                    config=dict(workload=workload, points=int(n[0] * n[1] * n[2]), faces_per_iteration=int(faces), domains=8,
+                                sample=cpu["sample"], same_size_as_gpu_arm=bool(abs(cpu_mp - args.mpoints) < 1e-9), variant=ref_variant),
                     cpu_baseline=cpu,
                     e2e=dict(value=cpu["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
@@ -188,6 +256,7 @@ def main():
     import torch
     import cfd_proxy_b200.mesh as M
     from cfd_proxy_b200.driver import session_from_env
+    from cfd_proxy_b200.lib import TRANSPORTS as L_TRANSPORTS
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the gradient/halo path has no CPU fallback")
@@ -232,9 +301,17 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # ---- timed region: K iterations of grad + halo (first, so that no other measurement pre-heats the part:
-    # under the 1 kW power cap the SM clock sags within a few hundred ms of load and this kernel is SM-side bound) ----
+    import math
+    # ---- first burst (cold part, boost clocks): kept as an extra key, NOT the headline ------------------------------
     S.iterate(args.variant, max(args.warmup, 3))
+    barrier()
+    ms_first = allmax(S.iterate(args.variant, args.steps)) / args.steps
+    # ---- steady state: under the 1 kW power cap the SM clock sags for the first seconds of load and this kernel is
+    # bound inside the SM, so the part is kept under load for `sustain-s` seconds before anything is timed ----
+    def n_for(seconds, ms_per_iter):
+        return max(args.steps, int(math.ceil(seconds * 1e3 / max(ms_per_iter, 1e-3))))
+    S.iterate(args.variant, n_for(args.sustain_s, ms_first))
+    # ---- timed region of the contract: exactly K iterations of grad + halo, barrier + synchronize on both sides ----
     barrier()
     l0 = S.stats().launches
     ms = S.iterate(args.variant, args.steps)
@@ -242,34 +319,45 @@ def main():
     launches = S.stats().launches - l0
     ms = allmax(ms)
     value = faces_total * args.steps / (ms * 1e-3)
+    # ---- the same over a region of >= sustain-s seconds (one CUDA-event pair around all of it) ----
+    n_sus = n_for(args.sustain_s, ms / args.steps)
+    barrier()
+    ms_sus = allmax(S.iterate(args.variant, n_sus))
+    sustained = dict(iterations=n_sus, seconds=ms_sus * 1e-3, ms_per_step=ms_sus / n_sus, value=faces_total * n_sus / (ms_sus * 1e-3))
+    transport = L_TRANSPORTS[int(S.stats().transport)]
 
-    # ---- kernel-only (comm_free) iterations: the roofline number -------------------------------
+    # ---- kernel-only (comm_free) iterations over >= sustain-s seconds: the roofline number ----------------------
     S.iterate("comm_free", max(args.warmup, 3))
     barrier()
-    ms_k = S.iterate("comm_free", args.steps) / args.steps
-    ms_k = allmax(ms_k)
+    n_k = n_for(args.sustain_s, ms / args.steps)
+    ms_k = allmax(S.iterate("comm_free", n_k)) / n_k
     peak, peak_src = measured_peak()
     alg = float(st.alg_bytes)                       # per GPU (this rank)
     achieved = alg / (ms_k * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes of one launch from an `ncu --set full` capture: quoted only for THIS build (hash of the kernel / schedule
+    # sources) and this workload; anything else is null rather than stale
+    traffic, traffic_src = None, None
     try:
         for ent in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["entries"]:
-            if abs(ent["alg_bytes"] - alg) / alg < 0.02:   # a capture of this very workload (per launch, per GPU)
-                traffic = ent["dram_bytes_per_launch"]
+            if ent.get("kernel_src_sha") == kernel_src_sha() and abs(ent["alg_bytes"] - alg) / alg < 0.02:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], ent.get("source")
     except Exception:
         pass
 
-    # ---- how much of the exchange is hidden: bulk-synchronous (compute, then exchange) vs overlapped.  Under the power
-    # cap the SM clock keeps sagging for seconds, so whatever is timed later looks slower: the three variants are timed
-    # in short interleaved bursts and compared by their medians. ----
-    bursts = {"comm_free": [], "mpi_bulk_sync": [], args.variant: []}
+    # ---- how much of the exchange is hidden: bulk-synchronous (compute, then exchange) vs overlapped, in short
+    # interleaved bursts compared by their medians (steady-state clocks by now) ----
+    bursts = {"comm_free": [], bulk_variant: [], args.variant: []}
     for _ in range(5):
         for v in bursts:
             S.iterate(v, 1)
             barrier()
             bursts[v].append(allmax(S.iterate(v, args.steps) / args.steps))
     med = {v: sorted(t)[len(t) // 2] for v, t in bursts.items()}
-    ms_kc, ms_bulk, ms_ovl = med["comm_free"], med["mpi_bulk_sync"], med[args.variant]
+    ms_kc, ms_bulk, ms_ovl = med["comm_free"], med[bulk_variant], med[args.variant]
+    bulk_transport = None
+    if world > 1:
+        S.iterate(bulk_variant, 1)
+        bulk_transport = L_TRANSPORTS[int(S.stats().transport)]
     # ---- the pseudo flux (flux.c), consumer of the exchanged gradients: its kernel alone, and the whole iteration of
     # solver.c:45-55 (gradient + halo + pseudo flux) on the device.  Reported beside the headline, not part of it. ----
     flux = None
@@ -311,19 +399,46 @@ def main():
         ms_e = allmax(ms_e)
         e2e = dict(value=faces_total * e2e_steps / (ms_e * 1e-3), unit=UNIT,
                    h2d_bytes_per_step=int(allsum(float(st.h2d_bytes))), d2h_bytes_per_step=int(allsum(float(st.d2h_bytes))),
-                   steps=e2e_steps, ms_per_step=ms_e / e2e_steps, wall_ms_per_step=wall / e2e_steps * 1e3)
+                   steps=e2e_steps, ms_per_step=ms_e / e2e_steps, wall_ms_per_step=wall / e2e_steps * 1e3,
+                   # both PCIe directions run concurrently (three-stream pipeline): bytes of this GPU / step time
+                   pcie_gbs_per_gpu=dict(h2d=float(st.h2d_bytes) / (ms_e / e2e_steps * 1e-3) / 1e9, d2h=float(st.d2h_bytes) / (ms_e / e2e_steps * 1e-3) / 1e9))
         S.lib.cfdp_set_resident(1)
+
+    # ---- what was timed is also checked: the own rows of the first hosted domain of rank 0, at full size, bit for bit
+    # against the oracle (skipped when the domain is too large for the CPU checker to finish in seconds) ----
+    verify = None
+    if rank == 0 and not args.no_parity:
+        d0 = S.domains[0]
+        if d0.sd.nownpoints <= 10_000_000:
+            try:
+                import numpy as np
+                from oracle import oracle as O
+                t_v = time.time()
+                S.iterate(args.variant, 1) if world == 1 else None     # several ranks: the last collective iteration stands
+                S.lib.cfdp_grad_to_host(__import__("ctypes").byref(d0.sd))
+                dom = d0.as_dict()
+                send0, _ = d0.index_lists()
+                want0 = O.gradients(dom, d0.var.copy(), is_send=O.is_send_mask(dom, send0), order=1)
+                nown = d0.sd.nownpoints
+                bad = int((d0.grad[:nown].view(np.uint64) != want0[:nown].view(np.uint64)).sum())
+                verify = dict(ok=bad == 0, mismatches=bad, words=int(nown) * 21, domain=int(d0.rank), seconds=round(time.time() - t_v, 1),
+                              what="own rows of one bench domain after the timed iterations vs oracle/gg_oracle.c (bit-exact)")
+            except Exception as ex:
+                verify = dict(ok=None, error=str(ex))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            cpu, _, _ = run_reference_sample(25, 1, mpoints=args.cpu_mpoints, variant=args.variant)
+            ref_variant = args.variant if args.variant.startswith("mpi") else "mpi_async"
+            cpu_mp = args.cpu_mpoints if args.cpu_mpoints else 2.0      # bounded sample: the full size runs in `--impl reference`
+            cpu, _, _ = run_reference_sample(args.steps, args.warmup, mpoints=cpu_mp, variant=ref_variant)   # same protocol as the reference arm
             if flux is not None and cpu.get("kind") == "reference":   # the reference's whole iteration (solver.c:45-55) on the same sample
-                cf, _, _ = run_reference_sample(25, 1, mpoints=args.cpu_mpoints, variant=args.variant, with_flux=True)
+                cf, _, _ = run_reference_sample(args.steps, args.warmup, mpoints=cpu_mp, variant=ref_variant, with_flux=True)
                 flux["cpu_reference_faces_per_s_grad_halo_flux"] = cf["value"]
         except Exception as ex:  # the baseline is reported, never required
             cpu = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="reference", sample=f"failed: {ex}")
 
+    line = None
     if rank == 0:
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -333,23 +448,41 @@ def main():
                         domains=8, domains_per_gpu=8 // world, point_order=args.order, tile_points=int(st.tile_points),
                         arithmetic="fma" if args.fma else "mul+add in the reference's single-thread order (bit-exact)",
                         l2="inputs larger than L2: %.1f GB read+written per iteration per GPU vs 126 MB L2" % (alg / 1e9),
+                        timing="steady state: %.1f s of iterations before the K timed steps (SM clock settled under the 1 kW power cap); first_burst = the same K steps on the cold part" % args.sustain_s,
+                        transport=transport, variant=args.variant,
                         setup_s=round(t_setup, 1), tiles=int(st.ntiles), boundary_tiles=int(st.nboundary_tiles),
-                        halo_rows_on_device=int(st.send_rows_local), halo_rows_over_nvlink=int(st.send_rows_remote)),
-            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                          kernel="gg_tile_pipe_kernel" if int(os.environ.get("CFDP_KERNEL", "2")) == 2 else "gg_tile_kernel", kernel_ms=ms_k, alg_bytes_per_launch=int(alg),
+                        halo_rows_on_device=int(st.send_rows_local), halo_rows_over_nvlink=int(st.send_rows_remote),
+                        device_gb=round(float(st.device_bytes) / 1e9, 2)),
+            first_burst=dict(ms_per_step=ms_first, value=faces_total / (ms_first * 1e-3)),
+            sustained=sustained,
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,
+                          kernel="gg_tile_pipe_kernel" if int(os.environ.get("CFDP_KERNEL", "2")) == 2 else "gg_tile_kernel", kernel_ms=ms_k,
+                          timed_launches=n_k, timed_region_s=ms_k * n_k * 1e-3, alg_bytes_per_launch=int(alg),
                           alg_bytes_per_face=alg / float(st.nfaces), peak_source=peak_src,
+                          # the kernel reads the packed halo rows on top of the algorithmic bytes (one contiguous copy per tile instead of a gather)
+                          packed_halo_bytes_per_launch=int(st.halo_pack_bytes), kernel_src_sha=kernel_src_sha(),
                           frac_of_8TBps_nominal=achieved / 8000.0, kernel_faces_per_s=float(st.nfaces) / (ms_k * 1e-3)),
             halo=dict(ms_comm_free=ms_kc, ms_bulk_sync=ms_bulk, ms_overlapped=ms_ovl,
                       exchange_ms=max(ms_bulk - ms_kc, 0.0),
                       hidden_frac=(1.0 - max(ms_ovl - ms_kc, 0.0) / (ms_bulk - ms_kc)) if (world > 1 and ms_bulk > ms_kc * 1.005) else None,
+                      transport_overlapped=transport, transport_bulk_sync=bulk_transport,
                       nvlink_bytes_per_iteration_per_gpu=int(st.send_rows_remote) * 168,
                       # the un-overlapped exchange (pack is fused into the kernel, so this is transfer + unpack) against NVLink 5: 900 GB/s per direction
                       nvlink_gbs=(int(st.send_rows_remote) * 168 / ((ms_bulk - ms_kc) * 1e-3) / 1e9) if (world > 1 and ms_bulk > ms_kc) else None,
                       nvlink_frac_of_900GBps=(int(st.send_rows_remote) * 168 / ((ms_bulk - ms_kc) * 1e-3) / 1e9 / 900.0) if (world > 1 and ms_bulk > ms_kc) else None,
-                      note="hidden_frac = 1 - (t_overlapped - t_comm_free) / (t_bulk_sync - t_comm_free); medians of 5 interleaved bursts per variant; variant timed: " + args.variant),
-            flux=flux, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
-        print(json.dumps(line))
+                      note="hidden_frac = 1 - (t_overlapped - t_comm_free) / (t_bulk_sync - t_comm_free); medians of 5 interleaved bursts per variant; overlapped variant: " + args.variant + ", bulk-synchronous variant: " + bulk_variant),
+            flux=flux, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks, verify=verify)
     S.close()
+    # ---- cross-GPU parity, visible to whoever reads the line: every variant on a small mesh with this run's topology ----
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_leg(world, rank, ("mpi_bulk_sync", "mpi_async", "gaspi_bulk_sync", "gaspi_async"))
+        except Exception as ex:
+            parity = dict(ok=None, error=str(ex))
+    if rank == 0:
+        line["parity"] = parity
+        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -178,15 +178,18 @@ def have_ref():
     return all(os.path.exists(os.path.join(REF_DIR, x)) for x in ("ref_harness", "mpirun_shim"))
 
 
-def run_ref(prefix, lvl, ndomains, variant, niter, outprefix, threads=1, repeats=1, timeout=600, with_flux=False):
-    """Run the reference harness (one rank per domain) and return per-domain grad/index/time (and psd_flux)."""
-    env = dict(os.environ, OMP_NUM_THREADS=str(threads), REF_WITH_FLUX="1" if with_flux else "0")
+def run_ref(prefix, lvl, ndomains, variant, niter, outprefix, threads=1, repeats=1, timeout=600, with_flux=False, timing_only=False):
+    """Run the reference harness (one rank per domain) and return per-domain grad/index/time (and psd_flux);
+    timing_only: no result dumps (large meshes), only the per-rank timing records."""
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), REF_WITH_FLUX="1" if with_flux else "0", REF_NO_DUMP="1" if timing_only else "0")
     cmd = [os.path.join(REF_DIR, "mpirun_shim"), "-np", str(ndomains), os.path.join(REF_DIR, "ref_harness"),
            "-lvl", str(lvl), prefix, variant, str(niter), outprefix, str(repeats)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"reference harness failed rc={r.returncode}\n{r.stdout}\n{r.stderr}")
     res = []
+    if timing_only:
+        return [dict(time=json.loads(open(f"{outprefix}_domain_{d}.time").read())) for d in range(ndomains)]
     for d in range(ndomains):
         g = np.fromfile(f"{outprefix}_domain_{d}.grad", dtype="<f8").reshape(-1, 7, 3)
         raw = np.fromfile(f"{outprefix}_domain_{d}.index", dtype="<i4")

@@ -130,12 +130,16 @@ int main(int argc, char *argv[])
   }
 
   char path[700];
+  const char *nd = getenv("REF_NO_DUMP");            /* timing runs on large meshes: no result dumps */
+  const int dump = !(nd && atoi(nd));
+  if (dump) {
   snprintf(path, sizeof path, "%s_domain_%d.grad", outprefix, cd.iProc);
   FILE *gf = fopen(path, "wb");
   ASSERT(gf != NULL);
   fwrite(&sd.grad[0][0][0], sizeof(double), (size_t)sd.nallpoints * NGRAD * 3, gf);
   fclose(gf);
-  if (with_flux) {
+  }
+  if (with_flux && dump) {
     snprintf(path, sizeof path, "%s_domain_%d.flux", outprefix, cd.iProc);
     FILE *ff = fopen(path, "wb");
     ASSERT(ff != NULL);
@@ -143,7 +147,7 @@ int main(int argc, char *argv[])
     fclose(ff);
   }
   snprintf(path, sizeof path, "%s_domain_%d.index", outprefix, cd.iProc);
-  dump_index(path, &cd);
+  if (dump) dump_index(path, &cd);
   snprintf(path, sizeof path, "%s_domain_%d.time", outprefix, cd.iProc);
   FILE *tf = fopen(path, "w");
   ASSERT(tf != NULL);

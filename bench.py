@@ -249,6 +249,13 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # hundreds of millions of points (BASELINE config 5): device-resident only -- no host mirrors of the results, mesh
+    # arrays released once the schedule is built, no pseudo-flux blobs, no host-buffer (e2e) leg
+    big = args.mpoints > 100.0
+    if big:
+        os.environ.setdefault("CFDP_LEAN_HOST", "1")
+        os.environ.setdefault("CFDP_FLUX_BLOB", "0")
+        args.no_e2e = args.no_flux = True
     # torchrun exports OMP_NUM_THREADS=1; the setup (mesh generation, face schedule) is OpenMP code: share the host cores
     if world > 1:
         os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
@@ -452,7 +459,8 @@ def main():
                         transport=transport, variant=args.variant,
                         setup_s=round(t_setup, 1), tiles=int(st.ntiles), boundary_tiles=int(st.nboundary_tiles),
                         halo_rows_on_device=int(st.send_rows_local), halo_rows_over_nvlink=int(st.send_rows_remote),
-                        device_gb=round(float(st.device_bytes) / 1e9, 2)),
+                        device_gb=round(float(st.device_bytes) / 1e9, 2),
+                        host_mode="lean: device-resident only, no host mirrors of grad, no e2e / pseudo-flux legs" if big else "host mirrors of var and grad (drop-in calls possible)"),
             first_burst=dict(ms_per_step=ms_first, value=faces_total / (ms_first * 1e-3)),
             sustained=sustained,
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,

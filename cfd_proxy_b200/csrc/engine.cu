@@ -527,20 +527,32 @@ extern "C" void cfdp_plan(void)
   for (Domain *d : E.doms) { ASSERT(d->threads_inited && d->sd != NULL); }
   const int nh = (int)E.doms.size();
 
-  /* 1. face schedules: domains in parallel when several are hosted */
+  /* 1. face schedules: domains side by side when several are hosted (the cores that are left over work inside each
+   * domain's builder, nested regions); very large domains one or two at a time: the builder needs ~0.5 KB per point */
+  const bool lean = env_int("CFDP_LEAN_HOST", 0) != 0;
+  long long total_pts = 0;
+  for (Domain *d : E.doms) total_pts += d->sd->nallpoints;
+  auto build_one = [&](int i) {
+    Domain *d = E.doms[(size_t)i];
+    build_schedule(d->sd, d->cd, E.sopt, d->sch);
+    if (lean) { /* the schedule holds everything the device needs: release the mesh arrays (CFDP_LEAN_HOST) */
+      free(d->sd->fpoint); free(d->sd->fnormal); d->sd->fpoint = nullptr; d->sd->fnormal = nullptr;
+      std::vector<int>().swap(d->sch.tile_face_ids); std::vector<int>().swap(d->sch.tile_halo_pts); /* introspection lists (cfdp_get_tile) */
+    }
+  };
   if (nh > 1) {
-    /* domains side by side, and the cores that are left over inside each domain's builder (nested regions) */
-    const int ncores = omp_get_max_threads(), outer = std::min(nh, ncores), inner = std::max(1, ncores / outer);
+    const int ncores = omp_get_max_threads();
+    const int outer = std::min(total_pts > 80000000LL ? 2 : nh, std::min(nh, ncores)), inner = std::max(1, ncores / outer);
     const int levels = omp_get_max_active_levels();
     if (inner > 1) omp_set_max_active_levels(std::max(levels, 2));
 #pragma omp parallel for schedule(dynamic, 1) num_threads(outer)
     for (int i = 0; i < nh; i++) {
       omp_set_num_threads(inner); /* this thread's nested regions */
-      build_schedule(E.doms[i]->sd, E.doms[i]->cd, E.sopt, E.doms[i]->sch);
+      build_one(i);
     }
     omp_set_max_active_levels(levels);
   } else {
-    build_schedule(E.doms[0]->sd, E.doms[0]->cd, E.sopt, E.doms[0]->sch);
+    build_one(0);
   }
 
   /* 2. unified rows and tile list: boundary tiles of all domains first */
@@ -550,7 +562,7 @@ extern "C" void cfdp_plan(void)
     E.ntiles += d->sch.ntiles; E.nbtiles += d->sch.nboundary;
     E.max_nfaces = std::max(E.max_nfaces, d->sch.max_nfaces); E.max_nloc = std::max(E.max_nloc, d->sch.max_nloc);
     for (int n : d->sch.tile_npts) E.max_npts = std::max(E.max_npts, n);
-    E.max_stage = std::max(E.max_stage, (size_t)d->sch.nall * CFDP_DIM2 * sizeof(double));
+    E.max_stage = std::max(E.max_stage, (size_t)d->sch.nall * (lean ? NGRAD : CFDP_DIM2) * sizeof(double));
     E.max_blob = std::max(E.max_blob, d->sch.max_blob);
     for (int n : d->sch.tile_nhpos) E.max_nhalo = std::max(E.max_nhalo, n);
     E.nfaces += d->sch.nfaces_computed; E.nown += d->sch.nown; E.nall += d->sch.nall;
@@ -837,6 +849,7 @@ extern "C" void cfdp_grad_to_host(solver_data *sd)
   ASSERT(E.committed);
   Domain *d = engine_find_domain(sd);
   ASSERT(d != NULL);
+  ASSERT(sd->grad != NULL); /* CFDP_LEAN_HOST: there is no host mirror of grad */
   const int i = hosted_index(d);
   const size_t n = (size_t)sd->nallpoints;
   launch_rows_copy(E.d_stage, nullptr, E.d_grad, (const uint32_t *)E.d_rowmap[i], (long long)n, CFDP_DIM2, E.s_comp);
@@ -853,6 +866,7 @@ extern "C" void cfdp_grad_to_device(solver_data *sd)
   ASSERT(d != NULL);
   const int i = hosted_index(d);
   const size_t n = (size_t)sd->nallpoints;
+  ASSERT(sd->grad != NULL); /* CFDP_LEAN_HOST: there is no host mirror of grad */
   CUDA_CHECK(cudaMemcpyAsync(E.d_stage, &sd->grad[0][0][0], n * CFDP_DIM2 * sizeof(double), cudaMemcpyHostToDevice, E.s_comp));
   launch_rows_copy(E.d_grad, (const uint32_t *)E.d_rowmap[i], E.d_stage, nullptr, (long long)n, CFDP_DIM2, E.s_comp);
 }
@@ -867,6 +881,7 @@ extern "C" void cfdp_flux_to_host(solver_data *sd)
   ASSERT(d != NULL);
   const int i = hosted_index(d);
   const size_t n = (size_t)sd->nownpoints;
+  ASSERT(sd->psd_flux != NULL); /* CFDP_LEAN_HOST: there is no host mirror of psd_flux */
   launch_rows_copy(E.d_stage, nullptr, E.d_flux, (const uint32_t *)E.d_rowmap[i], (long long)n, NFLUX, E.s_comp);
   CUDA_CHECK(cudaMemcpyAsync(&sd->psd_flux[0][0], E.d_stage, n * NFLUX * sizeof(double), cudaMemcpyDeviceToHost, E.s_comp));
   CUDA_CHECK(cudaStreamSynchronize(E.s_comp));
@@ -1312,6 +1327,7 @@ static void e2e_release(void)
 static void enqueue_step_e2e(int variant)
 {
   Engine &E = g_eng;
+  for (Domain *d : E.doms) ASSERT(d->sd->grad != NULL); /* host buffers in and out: not with CFDP_LEAN_HOST */
   e2e_setup();
   E2EResources &R = g_e2e;
   const bool exchange = variant != CFDP_COMM_FREE && have_exchange();
@@ -1492,6 +1508,7 @@ extern "C" int cfdp_get_tile(const solver_data *sd, int tile, int *face_ids, int
   Domain *d = engine_find_domain(sd);
   if (!d || !g_eng.planned || tile < 0 || tile >= d->sch.ntiles) return -1;
   const DomainSchedule &s = d->sch;
+  if (s.tile_face_ids.empty() && s.tile_faces > 0) return -1; /* released (CFDP_LEAN_HOST) */
   if (face_ids) memcpy(face_ids, &s.tile_face_ids[(size_t)s.tile_face_off[tile]], (size_t)s.tile_nfaces[tile] * sizeof(int));
   if (halo_points) memcpy(halo_points, &s.tile_halo_pts[(size_t)s.tile_halo_off[tile]], (size_t)s.tile_nhalo[tile] * sizeof(int));
   return s.tile_nfaces[tile];

@@ -320,6 +320,7 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
   __shared__ __align__(16) TileDesc s_desc[4];                  /* ring: descriptors of tiles i, i+1, i+2 of this CTA */
   __shared__ uint32_t s_eoff[4][2];                              /* ring: export list bounds of those tiles */
   __shared__ uint32_t s_exp[2 * CFDP_MAX_EXPORT];                /* this tile's export list: sources, then destinations */
+  __shared__ unsigned long long s_sigacc[CFDP_EXP_BASES - 2];    /* rows stored into each peer's memory and not yet signalled (thread 0 only) */
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   /* this CTA's tiles: t(i) = first + i*istride, i < count */
   const long long first = (long long)blockIdx.x * L.cstride;
@@ -359,6 +360,8 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
   if (tid == 0) {
     mbar_init(&full, 1);
     fence_mbar_init();
+#pragma unroll
+    for (int k = 0; k < CFDP_EXP_BASES - 2; k++) s_sigacc[k] = 0ull;
   }
   prefetch_desc(0); prefetch_desc(1);
   cp_async_commit(); cp_async_wait_all();
@@ -472,14 +475,10 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
         L.exp_base[sk >> 16][(size_t)dst * (NGRAD * 3) + c] = s_out[(sk & 0xFFFFu) * (NGRAD * 3) + c];
       }
       __syncthreads(); /* the staged rows have been read by every thread; the stores are ordered before thread 0's releases */
-      if (tid == 0 && L.sig_off) {
-        const uint32_t s0 = __ldg(L.sig_off + gt), s1 = __ldg(L.sig_off + gt + 1);
-        if (s1 > s0) {
-          __threadfence_system();
-          for (uint32_t s = s0; s < s1; s++) {
-            const uint32_t ent = __ldg(L.sig_ent + s);
-            signal_peer(L.sig_flag[ent & 15u], (unsigned long long)(ent >> 4));
-          }
+      if (tid == 0 && L.sig_off) { /* rows this tile stored into peer memory: signalled in one go per CTA, below */
+        for (uint32_t s = __ldg(L.sig_off + gt), s1 = __ldg(L.sig_off + gt + 1); s < s1; s++) {
+          const uint32_t ent = __ldg(L.sig_ent + s);
+          s_sigacc[ent & 15u] += (unsigned long long)(ent >> 4);
         }
       }
     }
@@ -489,6 +488,21 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
       if (has_next) {
         const uint32_t lo = CFDP_ZONE_BYTES * (uint32_t)warp, hi = min(min(lo + rows_w * CFDP_ROW_BYTES, out_cover), (uint32_t)nd.blob_bytes);
         if (lo < hi) bulk_g2s_a(sbase + lo, blob + nd.blob_off() + lo, hi - lo, bar, pol_stream);
+      }
+    }
+    /* direct halo stores: once this CTA has stored the rows of its last exporting tile it bumps the arrival counters of
+     * the peers (red.release.sys after a system fence: the stores of all threads were ordered before thread 0 by the
+     * barrier that ended the export).  One fence per CTA, not per tile: it costs an NVLink round trip, and it comes
+     * after the late fetch so that the next tile is not held up by it (threads.c:268-306: per partner counters). */
+    if (L.sig_off && tid == 0 && gt < L.nexport && (!has_next || L.tile_base + tile_of(i + 1) >= L.nexport)) {
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < CFDP_EXP_BASES - 2; k++) any = any || s_sigacc[k] != 0ull;
+      if (any) {
+        __threadfence_system();
+#pragma unroll
+        for (int k = 0; k < CFDP_EXP_BASES - 2; k++)
+          if (s_sigacc[k]) { signal_peer(L.sig_flag[k], s_sigacc[k]); s_sigacc[k] = 0ull; }
       }
     }
     /* boundary tiles: their rows may be consumed by the exchange as soon as every boundary tile has retired (the

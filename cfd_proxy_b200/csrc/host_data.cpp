@@ -27,6 +27,11 @@ static void *xmalloc(size_t bytes)
   return p;
 }
 
+/* CFDP_LEAN_HOST=1 (device-resident runs on meshes of hundreds of millions of points): the host mirrors of the RESULTS
+ * (sd->grad, sd->psd_flux: 192 bytes per point) are not allocated, and the mesh arrays sd->fpoint / sd->fnormal are
+ * released once the GPU schedule has been built from them (cfdp_plan).  Entry points that need them fail loudly. */
+static bool lean_host(void) { const char *e = getenv("CFDP_LEAN_HOST"); return e && atoi(e) != 0; }
+
 /* ---------------------------------------------------------------------------------------- */
 extern "C" void read_solver_data(int ncid, solver_data *sd)
 {
@@ -47,8 +52,10 @@ extern "C" void read_solver_data(int ncid, solver_data *sd)
   sd->pvolume = (double *)xmalloc(na * sizeof(double));
   /* var / grad cross PCIe every drop-in call: page-locked when a CUDA device is present */
   sd->var = (double(*)[NGRAD])engine_alloc_pinned(na * NGRAD * sizeof(double));
-  sd->grad = (double(*)[NGRAD][3])engine_alloc_pinned(na * NGRAD * 3 * sizeof(double));
-  sd->psd_flux = (double(*)[NFLUX])xmalloc(na * NFLUX * sizeof(double));
+  if (!lean_host()) {
+    sd->grad = (double(*)[NGRAD][3])engine_alloc_pinned(na * NGRAD * 3 * sizeof(double));
+    sd->psd_flux = (double(*)[NFLUX])xmalloc(na * NFLUX * sizeof(double));
+  }
   get_nc_int(ncid, "fpoint", &sd->fpoint[0][0]);
   get_nc_double(ncid, "fnormal", &sd->fnormal[0][0]);
   get_nc_double(ncid, "pvolume", sd->pvolume);
@@ -65,8 +72,8 @@ extern "C" void init_solver_data(solver_data *sd, int NITER)
 #pragma omp parallel for schedule(static)
   for (long long i = 0; i < na; i++) {
     for (int j = 0; j < NGRAD; j++) sd->var[i][j] = 1.0;
-    for (int j = 0; j < NGRAD; j++) for (int k = 0; k < 3; k++) sd->grad[i][j][k] = 1.0;
-    for (int j = 0; j < NFLUX; j++) sd->psd_flux[i][j] = 1.0;
+    if (sd->grad) for (int j = 0; j < NGRAD; j++) for (int k = 0; k < 3; k++) sd->grad[i][j][k] = 1.0;
+    if (sd->psd_flux) for (int j = 0; j < NFLUX; j++) sd->psd_flux[i][j] = 1.0;
   }
   sd->niter = NITER;
 }
@@ -154,8 +161,10 @@ extern "C" void cfdp_attach_mesh(const cfdp_mesh_domain *m, comm_data *cd, solve
   sd->fnormal = (double(*)[3])xmalloc(nf * 3 * sizeof(double));
   sd->pvolume = (double *)xmalloc(na * sizeof(double));
   sd->var = (double(*)[NGRAD])engine_alloc_pinned(na * NGRAD * sizeof(double));
-  sd->grad = (double(*)[NGRAD][3])engine_alloc_pinned(na * NGRAD * 3 * sizeof(double));
-  sd->psd_flux = (double(*)[NFLUX])xmalloc(na * NFLUX * sizeof(double));
+  if (!lean_host()) {
+    sd->grad = (double(*)[NGRAD][3])engine_alloc_pinned(na * NGRAD * 3 * sizeof(double));
+    sd->psd_flux = (double(*)[NFLUX])xmalloc(na * NFLUX * sizeof(double));
+  }
   memcpy(sd->fpoint, m->fpoint, nf * 2 * sizeof(int));
   memcpy(sd->fnormal, m->fnormal, nf * 3 * sizeof(double));
   memcpy(sd->pvolume, m->pvolume, na * sizeof(double));

@@ -123,8 +123,12 @@ struct TileBuilder {
 
 } // namespace
 
+static double wall(void) { return omp_get_wtime(); }
 void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOptions &opt, DomainSchedule &out)
 {
+  const bool prof = getenv("CFDP_SCHED_PROF") != nullptr;
+  double t_prev = wall();
+  auto lap = [&](const char *what) { if (prof) { const double t = wall(); fprintf(stderr, "  schedule[%d pts] %-28s %.2f s\n", sd->nownpoints, what, t - t_prev); t_prev = t; } };
   const int nown = sd->nownpoints, nall = sd->nallpoints;
   ASSERT(nown > 0 && nall >= nown);
   ASSERT(opt.tile_points >= 16 && opt.tile_points <= CFDP_MAX_TILE_POINTS && opt.tile_points % 16 == 0);
@@ -147,6 +151,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
   Csr g;
   build_csr(sd, g, out.nfaces_computed);
 
+  lap("csr");
   /* ---- 1. group own points into tiles ---- */
   TileBuilder tb(g, opt, nown, nall);
   if (opt.order == 1) {
@@ -211,6 +216,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
     for (int t = 0; t < ntiles; t++) std::sort(tb.pts.begin() + tb.tile_pt_off[t], tb.pts.begin() + tb.tile_pt_off[(size_t)t + 1]);
   }
 
+  lap("tiling");
   /* ---- 1b. own rows by shared-memory bank.  A tile point is a lane of the face walk AND a var row other lanes
    * gather.  Permuting the points inside a block of 16 consecutive positions keeps every half-warp's membership (so
    * the sets of rows read together do not change) but lets each point pick the bank-pair class (position mod 16)
@@ -384,6 +390,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
     }
   }
 
+  lap("own-row placement (1b)");
   /* ---- 2. boundary tiles first, rows ---- */
   std::vector<int> tile_bnd((size_t)ntiles, 0), order((size_t)ntiles);
   for (int t = 0; t < ntiles; t++)
@@ -415,6 +422,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
   for (int k = 0; k < ntiles; k++)
     for (int i = 0; i < out.tile_npts[k]; i++) tile_of_new[tb.pts[pt_off[k] + i]] = k;
 
+  lap("rows");
   /* ---- 3. per tile: face ids, halo points ---- */
   /* eslot[e] for adjacency entry e: tile-local id of its face inside the tile of the entry's point
    * (ids in discovery order; the shared-memory slot is chosen later) */
@@ -477,6 +485,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
   }
   out.blob.assign((size_t)out.tile_blob[ntiles], 0);
 
+  lap("pass A (counts)");
   /* pass B: order every point's faces, place face slots and halo rows by shared-memory bank, emit blobs */
   const bool place_by_bank = opt.bank_placement != 0;
   std::vector<std::vector<unsigned char>> ftile_bytes(opt.flux_blob ? (size_t)ntiles : 0);
@@ -492,8 +501,12 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
     std::vector<int> grp_off, grp_list;          /* per face / per halo point: distinct groups */
     std::vector<int> cls; std::vector<std::vector<int>> members; /* class of an object; objects of a class */
     std::vector<Ent> ftile_ents; std::vector<int> fdeg, fface_of, fhalo_of, fslot_of, fhpos_of; std::vector<unsigned char> fghost; /* pseudo-flux blob */
-#pragma omp for schedule(dynamic, 16)
+    double tB[6] = {0, 0, 0, 0, 0, 0}; double tb0 = 0;
+    const bool tprof = prof && omp_get_thread_num() == 0;
+#define TB(i) do { if (tprof) { const double t_ = wall(); tB[i] += t_ - tb0; tb0 = t_; } } while (0)
+#pragma omp for schedule(dynamic, 16) nowait
     for (int k = 0; k < ntiles; k++) {
+      if (tprof) tb0 = wall();
       const int n = out.tile_npts[k], nf = out.tile_nfaces[k], nh = tnh[k], md = tmaxdeg[k];
       const int nslots = out.tile_nslots[k], nhpos = out.tile_nhpos[k], n_even = CFDP_HALO_BASE(n);
       const uint32_t npad = (uint32_t)align_up((size_t)n, 32);
@@ -549,6 +562,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
       }
       for (int i = 0; i < n; i++) lmap[P[i]] = -1;
       for (int j = 0; j < nh; j++) lmap[hpts[j]] = -1;
+      TB(0);
 
       /* ---- placement.  A half-warp (16 lanes = 16 consecutive tile points) at step j of the face walk
        * reads one normal and one var row per lane with 8-byte loads; two lanes collide when they read different
@@ -604,7 +618,18 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
           const int cap = npos / 16;
           int used[16] = {0};
           cls.assign((size_t)nobj, -1);
+          std::vector<int> gmx;
           for (int o = 0; o < nobj; o++) {
+            /* the fullest class of each group this object is read in: once per object, not once per candidate class */
+            gmx.assign((size_t)(grp_off[(size_t)o + 1] - grp_off[o]), 0);
+            for (int t = grp_off[o]; t < grp_off[(size_t)o + 1]; t++) {
+              const int gi = grp_list[t];
+              if (gi < 0) continue;
+              const unsigned char *cc = &cnt[(size_t)gi * 16];
+              int mx = 0;
+              for (int x = 0; x < 16; x++) mx = std::max(mx, (int)cc[x]);
+              gmx[(size_t)(t - grp_off[o])] = mx;
+            }
             int best = -1, best_cost = 1 << 30;
             for (int c0 = 0; c0 < 16; c0++) {
               const int c = (c0 + o) & 15; /* rotate the tie-break so that classes fill evenly */
@@ -613,11 +638,9 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
               for (int t = grp_off[o]; t < grp_off[(size_t)o + 1]; t++) {
                 const int gi = grp_list[t];
                 if (gi < 0) continue;
-                const unsigned char *cc = &cnt[(size_t)gi * 16];
-                int mx = 0;
-                for (int x = 0; x < 16; x++) mx = std::max(mx, (int)cc[x]);
-                if (cc[c] + 1 > mx) cost += 4;          /* raises this group's wavefront count */
-                cost += cc[c];                          /* prefer emptier classes */
+                const int ccc = cnt[(size_t)gi * 16 + c];
+                if (ccc + 1 > gmx[(size_t)(t - grp_off[o])]) cost += 4;          /* raises this group's wavefront count */
+                cost += ccc;                            /* prefer emptier classes */
               }
               if (cost < best_cost) { best_cost = cost; best = c; }
             }
@@ -703,6 +726,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
       }
       };
       place_all(tile_ents, deg, md, nh, nf, hpos_of, nhpos, slot_of, nslots);
+      TB(1);
 
       /* ---- emit */
       {
@@ -728,6 +752,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
           ell[(size_t)j * npad + i] = loc | ghost | ((uint32_t)slot_of[e.fid] << 16) | (e.sign << 31);
         }
 
+      TB(2);
       /* ---- the pseudo-flux blob of the tile (flux.c:179-190 with one thread): an own point receives -flux from the
        * faces where it is p1 and +flux from the faces where it is p0 and p1 is a ghost; nothing else is stored.
        * Face slots and halo positions are placed by bank for this adjacency like those of the gradient blob. */
@@ -787,6 +812,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
         out.ftile_nfaces[k] = nfslots; out.ftile_nhalo[k] = nfhpos; out.ftile_maxdeg[k] = fmd;
       }
 
+      TB(3);
       /* shared-memory wavefront estimate of the face walk: 7 var words + 3 normal words per face end */
       for (int w0 = 0; w0 < n; w0 += 16)
         for (int j = 0; j < md; j++) {
@@ -811,8 +837,12 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
           for (int c = 0; c < 16; c++) { mv = std::max(mv, cnt_v[c]); mn = std::max(mn, cnt_n[c]); }
           wf_min_total += 10; wf_est_total += 7 * mv + 3 * mn;
         }
+      TB(4);
     }
+    if (tprof) fprintf(stderr, "  pass B thread 0: entries+sort %.2f  place %.2f  emit %.2f  flux blob %.2f  estimate %.2f s\n", tB[0], tB[1], tB[2], tB[3], tB[4]);
+#undef TB
   }
+  lap("pass B (placement + emit)");
   out.lds_wavefronts_min = wf_min_total; out.lds_wavefronts_est = wf_est_total;
   if (opt.flux_blob) {
     out.ftile_blob.assign((size_t)ntiles + 1, 0);

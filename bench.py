@@ -411,6 +411,30 @@ def main():
                    pcie_gbs_per_gpu=dict(h2d=float(st.h2d_bytes) / (ms_e / e2e_steps * 1e-3) / 1e9, d2h=float(st.d2h_bytes) / (ms_e / e2e_steps * 1e-3) / 1e9))
         S.lib.cfdp_set_resident(1)
 
+    # ---- what the platform gives a plain pinned copy, both directions at once, on every rank at the same time: the
+    # ceiling of the host-buffer path (at N > 1 the ranks share the host's memory system and PCIe root) ----
+    if e2e is not None:
+        try:
+            nb = 1 << 30
+            hsrc = torch.empty(nb, dtype=torch.uint8).pin_memory(); hdst = torch.empty(nb, dtype=torch.uint8).pin_memory()
+            dsrc = torch.empty(nb, dtype=torch.uint8, device="cuda"); ddst = torch.empty(nb, dtype=torch.uint8, device="cuda")
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            for rep in range(2):
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                with torch.cuda.stream(s1):
+                    ev[0].record(); ddst.copy_(hsrc, non_blocking=True); ev[1].record()
+                with torch.cuda.stream(s2):
+                    ev[2].record(); hdst.copy_(dsrc, non_blocking=True); ev[3].record()
+                torch.cuda.synchronize()
+            e2e["pcie_probe_gbs_per_gpu"] = dict(h2d=nb / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9, d2h=nb / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9,
+                                                 note="1 GiB pinned copies, both directions at once, all ranks simultaneously")
+            del hsrc, hdst, dsrc, ddst
+        except Exception as ex:
+            e2e["pcie_probe_gbs_per_gpu"] = dict(error=str(ex))
+
     # ---- what was timed is also checked: the own rows of the first hosted domain of rank 0, at full size, bit for bit
     # against the oracle (skipped when the domain is too large for the CPU checker to finish in seconds) ----
     verify = None
@@ -484,6 +508,8 @@ def main():
     # ---- cross-GPU parity, visible to whoever reads the line: every variant on a small mesh with this run's topology ----
     parity = None
     if not args.no_parity:
+        for k in ("CFDP_LEAN_HOST", "CFDP_FLUX_BLOB"):      # the parity mesh is small: host mirrors as usual
+            os.environ.pop(k, None)
         try:
             parity = parity_leg(world, rank, ("mpi_bulk_sync", "mpi_async", "gaspi_bulk_sync", "gaspi_async"))
         except Exception as ex:

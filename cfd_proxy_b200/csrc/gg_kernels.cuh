@@ -381,6 +381,17 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
     const TileDesc td = s_desc[i & 3];
     const int npts = td.npts;
     prefetch_desc(i + 2);
+    /* export list of this tile (boundary tiles): fetched now, it lands during the face walk */
+    const int gt = L.tile_base + t;
+    const uint32_t e0 = gt < L.nexport ? s_eoff[i & 3][0] : 0u;
+    const int nexp = gt < L.nexport ? (int)(s_eoff[i & 3][1] - e0) : 0;
+    const bool exp_in_smem = nexp > 0 && nexp <= CFDP_MAX_EXPORT;
+    if (exp_in_smem) {
+      for (int k = tid; k < nexp; k += nthr) {
+        cp_async4(&s_exp[k], L.exp_src + e0 + k);
+        cp_async4(&s_exp[CFDP_MAX_EXPORT + k], L.exp_dst + e0 + k);
+      }
+    }
     cp_async_commit();
 
     double acc[NGRAD * 3];
@@ -429,18 +440,6 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
       nd = s_desc[(i + 1) & 3];
       if (tid == 0) bulk_early(nd, out_cover < nd.blob_bytes ? out_cover : nd.blob_bytes);
     }
-    /* export list of this tile, fetched asynchronously while the rows are being staged */
-    const int gt = L.tile_base + t;
-    const uint32_t e0 = gt < L.nexport ? s_eoff[i & 3][0] : 0u;
-    const int nexp = gt < L.nexport ? (int)(s_eoff[i & 3][1] - e0) : 0;
-    const bool exp_in_smem = nexp > 0 && nexp <= CFDP_MAX_EXPORT;
-    if (exp_in_smem) {
-      for (int k = tid; k < nexp; k += nthr) {
-        cp_async4(&s_exp[k], L.exp_src + e0 + k);
-        cp_async4(&s_exp[CFDP_MAX_EXPORT + k], L.exp_dst + e0 + k);
-      }
-    }
-    cp_async_commit();
     long long q1 = 0, q2 = 0, q3 = 0;
     if (L.prof && tid == 0) q1 = clock64();
 
@@ -464,7 +463,7 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
       /* fused pack (threads.c:187-249, :791-813) / direct halo stores: the rows of this tile that other domains need go
        * straight from the staged rows to their consumers: the packed send buffer, the ghost rows of a domain hosted on
        * this GPU, or the ghost rows of a domain on a peer GPU (CUDA IPC mapping, stores over NVLink) */
-      cp_async_wait_all(); /* the export list (and the descriptor prefetch) */
+      cp_async_wait_all(); /* the export list, requested before the face walk */
       __syncthreads();
       const double *s_out = reinterpret_cast<const double *>(smem);
       const int nw = nexp * (NGRAD * 3);

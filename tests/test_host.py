@@ -280,3 +280,26 @@ def test_fused_pack_export_lists_cover_every_halo_row_once(session_factory, n, p
             got[key] = (sd.value, sp.value)
     assert got == want
     assert st.send_rows_local == len(want)
+
+
+def test_lean_host_mode_releases_mesh_arrays(session_factory, monkeypatch):
+    """CFDP_LEAN_HOST=1 (256 M-point device-resident runs): no host mirrors of grad / psd_flux, fpoint / fnormal are
+    released once the schedule is built; the plan itself is unchanged."""
+    spec = M.make_spec((16, 14, 12), (2, 2, 1), order="lex", hexfrac=0.3)
+    S = session_factory(4, tile_points=64)
+    S.load_spec(spec)
+    S.setup(device=False)
+    ref = S.stats()
+    ref_tiles = [S.schedule(d)["tile_row0"].copy() for d in S.domains]
+    monkeypatch.setenv("CFDP_LEAN_HOST", "1")
+    S = session_factory(4, tile_points=64)
+    S.load_spec(spec)
+    for d in S.domains:
+        assert not d.sd.grad and not d.sd.psd_flux and d.sd.fpoint and d.sd.var
+    S.setup(device=False)
+    st = S.stats()
+    for d in S.domains:
+        assert not d.sd.fpoint and not d.sd.fnormal
+    assert (st.nfaces, st.ntiles, st.rows, st.blob_bytes) == (ref.nfaces, ref.ntiles, ref.rows, ref.blob_bytes)
+    for d, t0 in zip(S.domains, ref_tiles):
+        assert np.array_equal(S.schedule(d)["tile_row0"], t0)

@@ -37,7 +37,7 @@ def main():
             t_w = time.time()
             while time.time() - t_w < warm_s:
                 S.iterate("comm_free", 20)
-            res = {kc: dict(k=[], a=[]) for kc in kcfgs.split(",")}
+            res = {kc: dict(k=[], a=[], b=[]) for kc in kcfgs.split(",")}
             for rnd in range(rounds):     # configurations interleaved: drift hits all of them alike
                 for kc in res:
                     ver, chunk, pers, order = (int(x) for x in (kc.split(".") + ["0"])[:4])
@@ -46,9 +46,10 @@ def main():
                     S.iterate("comm_free", 2)
                     res[kc]["k"].append(S.iterate("comm_free", iters) / iters)
                     res[kc]["a"].append(S.iterate("mpi_async", iters) / iters)
+                    res[kc]["b"].append(S.iterate("mpi_bulk_sync", iters) / iters)
             st = S.stats()
             for kc, r in res.items():
-                ms, ms_a = sorted(r["k"])[len(r["k"]) // 2], sorted(r["a"])[len(r["a"]) // 2]
+                ms, ms_a, ms_b = sorted(r["k"])[len(r["k"]) // 2], sorted(r["a"])[len(r["a"]) // 2], sorted(r["b"])[len(r["b"]) // 2]
                 prof = None
                 if os.environ.get("CFDP_PHASE_PROF"):
                     ver, chunk, pers, order = (int(x) for x in (kc.split(".") + ["0"])[:4])
@@ -56,12 +57,12 @@ def main():
                     S.lib.cfdp_set_kernel(ver, chunk, pers)
                     buf = (C.c_ulonglong * 8)()
                     S.lib.cfdp_get_phase_profile(buf, 1)
-                    S.iterate("comm_free", 5)
+                    S.iterate(os.environ.get("KBENCH_PROF_VARIANT", "comm_free"), 5)
                     S.lib.cfdp_get_phase_profile(buf, 1)
                     nt = max(buf[4], 1)
                     prof = dict(wait=round(buf[0] / nt), walk=round(buf[1] / nt), rest=round(buf[2] / nt), early=round(buf[5] / nt), stage_store=round(buf[6] / nt), wait_read=round(buf[7] / nt))
                 print(json.dumps(dict(mesh=head, kernel=kc, kernel_ms=round(ms, 4), spread=[round(min(r["k"]), 4), round(max(r["k"]), 4)], gfaces=round(st.nfaces / ms / 1e6, 2), frac=round(st.alg_bytes / ms / 1e6 / peak, 4),
-                                      async_ms=round(ms_a, 4), smem=st.smem_bytes, tiles=st.ntiles, dup=round(st.tile_faces / st.nfaces, 3),
+                                      async_ms=round(ms_a, 4), bulk_ms=round(ms_b, 4), boundary_tiles=st.nboundary_tiles, smem=st.smem_bytes, tiles=st.ntiles, dup=round(st.tile_faces / st.nfaces, 3),
                                       blob_B_per_face=round(st.blob_bytes / st.nfaces, 2), setup_s=round(setup_s, 1), phase=prof)), flush=True)
             if os.environ.get("KBENCH_FLUX"):
                 S.flux_iterate(3)

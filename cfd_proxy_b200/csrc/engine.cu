@@ -24,6 +24,10 @@
 #include <dlfcn.h>
 #include <string.h>
 #include <unistd.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <time.h>
+#include <sys/stat.h>
 #include <algorithm>
 #include <map>
 #include <mutex>
@@ -289,29 +293,54 @@ extern "C" int cfdp_nccl_init(const void *id128)
   return 0;
 }
 
-/* pure-C drivers (no Python plumbing): rank 0 publishes the id in a file named after the rendezvous port */
+/* pure-C drivers (no Python plumbing): rank 0 publishes the NCCL id in a file.  The file lives in a per-user 0700
+ * directory, is created with O_EXCL under a temporary name and renamed into place, carries a magic word, the launcher's
+ * pid and a timestamp that readers check (a stale file of an earlier run under a recycled pid / port is ignored), and is
+ * unlinked by rank 0 once every rank has joined the communicator. */
+struct NcclIdFile { unsigned long long magic; long long ppid; long long t_sec; nccl_uid id; };
 static void nccl_file_bootstrap(void)
 {
   Engine &E = g_eng;
   if (E.nprocs == 1 || E.comm) return;
-  char path[512];
+  char dir[400], path[512];
   const char *f = getenv("CFDP_NCCL_ID_FILE");
   if (f && *f) snprintf(path, sizeof path, "%s", f);
-  else snprintf(path, sizeof path, "/tmp/cfdp_nccl_id_%s_%d", getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "29500", (int)getppid());
-  nccl_uid id;
+  else {
+    const char *base = getenv("XDG_RUNTIME_DIR");
+    snprintf(dir, sizeof dir, "%s/cfdp_b200_%d", (base && *base) ? base : "/tmp", (int)getuid());
+    if (mkdir(dir, 0700) != 0 && errno != EEXIST) { fprintf(stderr, "Error: cannot create %s [%s:%i]\n", dir, __FILE__, __LINE__); exit(EXIT_FAILURE); }
+    struct stat sb;
+    ASSERT(stat(dir, &sb) == 0 && S_ISDIR(sb.st_mode) && sb.st_uid == getuid() && (sb.st_mode & 077) == 0); /* ours, private */
+    snprintf(path, sizeof path, "%s/nccl_id_%s_%d", dir, getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "29500", (int)getppid());
+  }
+  const unsigned long long MAGIC = 0x4346445042323030ull; /* "CFDPB200" */
+  NcclIdFile rec;
   if (E.proc_rank == 0) {
-    cfdp_nccl_get_unique_id(&id);
-    char tmp[600]; snprintf(tmp, sizeof tmp, "%s.tmp", path);
-    FILE *fp = fopen(tmp, "wb"); ASSERT(fp != NULL);
-    ASSERT(fwrite(&id, sizeof id, 1, fp) == 1); fclose(fp);
+    memset(&rec, 0, sizeof rec);
+    rec.magic = MAGIC; rec.ppid = (long long)getppid(); rec.t_sec = (long long)time(NULL);
+    cfdp_nccl_get_unique_id(&rec.id);
+    char tmp[600]; snprintf(tmp, sizeof tmp, "%s.tmp.%d", path, (int)getpid());
+    unlink(path);                                            /* whatever an earlier run left behind */
+    const int fd = open(tmp, O_WRONLY | O_CREAT | O_EXCL, 0600);
+    ASSERT(fd >= 0);
+    ASSERT(write(fd, &rec, sizeof rec) == (ssize_t)sizeof rec);
+    close(fd);
     ASSERT(rename(tmp, path) == 0);
   } else {
-    FILE *fp = nullptr;
-    for (int i = 0; i < 6000 && !(fp = fopen(path, "rb")); i++) usleep(10000);
-    ASSERT(fp != NULL);
-    ASSERT(fread(&id, sizeof id, 1, fp) == 1); fclose(fp);
+    bool ok = false;
+    for (int i = 0; i < 6000 && !ok; i++) {
+      FILE *fp = fopen(path, "rb");
+      if (fp) {
+        ok = fread(&rec, sizeof rec, 1, fp) == 1 && rec.magic == MAGIC && rec.ppid == (long long)getppid() &&
+             llabs((long long)time(NULL) - rec.t_sec) < 600;  /* this launch, not a leftover */
+        fclose(fp);
+      }
+      if (!ok) usleep(10000);
+    }
+    ASSERT(ok);
   }
-  cfdp_nccl_init(&id);
+  cfdp_nccl_init(&rec.id);                                   /* collective: returns when every rank has joined */
+  if (E.proc_rank == 0) unlink(path);
 }
 
 /* setup-time exchange of int messages with other processes (comm_data.c:195-250).  Default
@@ -815,7 +844,13 @@ extern "C" void cfdp_commit(void)
   E.d_send_rows = upload(E.h_send_rows); E.d_recv_rows = upload(E.h_recv_rows);
   CUDA_CHECK(cudaMalloc(&E.d_sendbuf, (size_t)std::max<long long>(E.n_send, 1) * CFDP_DIM2 * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&E.d_recvbuf, (size_t)std::max<long long>(E.n_recv, 1) * CFDP_DIM2 * sizeof(double)));
-  if (!E.peers.empty() && !E.comm && !g_int_exchange) nccl_file_bootstrap();
+  if (!E.peers.empty() && !E.loopback && !E.comm) {
+    if (g_int_exchange) { /* the host plumbing carried the setup handshake itself (cfdp_set_int_exchange) but never called cfdp_nccl_init */
+      fprintf(stderr, "Error: %d peer GPU(s) but no NCCL communicator: call cfdp_nccl_init() before cfdp_commit() [%s:%i]\n", (int)E.peers.size(), __FILE__, __LINE__);
+      exit(EXIT_FAILURE);
+    }
+    nccl_file_bootstrap();
+  }
   if (!E.peers.empty() && env_int("CFDP_IPC", 1)) ipc_setup();
   CUDA_CHECK(cudaDeviceSynchronize());
   E.committed = true;
@@ -1652,7 +1687,10 @@ extern "C" void cfdp_finalize(void)
       free(cd->sendindex); free(cd->recvindex); free(cd->commpartner); free(cd->sendcount); free(cd->recvcount);
       free(cd->addpoint_owner); free(cd->addpoint_id); free(cd->local_recv_offset); free(cd->local_send_offset);
       free(cd->remote_recv_offset); free(cd->notification); free((void *)cd->recv_flag); free((void *)cd->send_flag);
-      memset(cd, 0, sizeof *cd);
+      /* the struct is the caller's: only the pointers this library allocated are reset */
+      cd->sendindex = cd->recvindex = nullptr; cd->commpartner = cd->sendcount = cd->recvcount = nullptr;
+      cd->addpoint_owner = cd->addpoint_id = nullptr; cd->local_recv_offset = cd->local_send_offset = cd->remote_recv_offset = nullptr;
+      cd->notification = nullptr; cd->recv_flag = cd->send_flag = nullptr;
     }
     delete d;
   }
@@ -1660,6 +1698,12 @@ extern "C" void cfdp_finalize(void)
   if (E.pipe.prof) { cudaFree(E.pipe.prof); E.pipe.prof = nullptr; E.pipe4.prof = nullptr; }
   if (E.d_progress) { cudaFree(E.d_progress); E.d_progress = nullptr; }
   e2e_release();
+  if (E.have_device) { /* a later cfdp_configure() may name another device: nothing of this one survives */
+    cudaStreamDestroy(E.s_comp); cudaStreamDestroy(E.s_comm); E.s_comp = E.s_comm = nullptr;
+    cudaEventDestroy(E.ev_b); cudaEventDestroy(E.ev_x); cudaEventDestroy(E.ev_t0); cudaEventDestroy(E.ev_t1);
+    E.ev_b = E.ev_x = E.ev_t0 = E.ev_t1 = nullptr;
+    E.have_device = false;
+  }
 
   E.d_var = E.d_grad = E.d_pvol = nullptr; E.d_blob = nullptr; E.d_tiles = nullptr; E.d_stage = nullptr;
   E.d_loc_dst = E.d_loc_src = E.d_send_rows = E.d_recv_rows = nullptr; E.d_sendbuf = E.d_recvbuf = nullptr;

@@ -149,6 +149,7 @@ int cfdp_nc_open(const char *path, int mode, int *ncidp)
       for (uint32_t d = 0; d < nd; d++) {
         uint32_t di = get32(&c);
         if (c.bad || (int)di >= f->ndims) goto fail;
+        if (f->dims[di].len != 0 && v->nelem > (uint64_t)-1 / 16 / f->dims[di].len) { rc = NCE_TRUNC; goto fail; } /* crafted header: product overflows */
         v->nelem *= f->dims[di].len;
       }
       skip_att_list(&c);
@@ -156,7 +157,8 @@ int cfdp_nc_open(const char *path, int mode, int *ncidp)
       (void)get32(&c); /* vsize: redundant (and saturated for >4 GiB variables) */
       v->begin = wide ? get64(&c) : get32(&c);
       if (c.bad || nc_type_size(v->type) == 0) goto fail;
-      if (v->begin + v->nelem * nc_type_size(v->type) > f->size) { rc = NCE_TRUNC; goto fail; }
+      /* overflow-checked: nelem * size cannot wrap (bounded above), begin is compared without adding to it */
+      if (v->begin > f->size || v->nelem * nc_type_size(v->type) > f->size - v->begin) { rc = NCE_TRUNC; goto fail; }
     }
     f->nvars = (int)n;
   }

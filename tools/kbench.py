@@ -23,7 +23,11 @@ def main():
     peak, _ = measured_peak()
     for mesh in args:
         head, kcfgs = mesh.split("/")
-        tile, order, fma = head.split(":")
+        tile, order, fma, budget = (head.split(":") + ["0"])[:4]
+        if int(budget):
+            os.environ["CFDP_STAGE_BUDGET"] = budget
+        else:
+            os.environ.pop("CFDP_STAGE_BUDGET", None)
         t0 = time.time()
         with Session(f6 or 8, device=0, tile_points=int(tile), tile_order=1 if order == "brickid" else 0) as S:
             if f6:   # BASELINE configs[1]/[2]: F6-like stand-in (hybrid hex/tet dual, ~2 M points at level 1), all domains on one GPU

@@ -47,6 +47,9 @@ struct TileDesc {
 /* tile-local point index: [0,npts) own points of the tile, halo points from CFDP_HALO_BASE(npts) on
  * (even, so that the own var rows can be fetched as one 16-byte granular bulk copy) */
 #define CFDP_HALO_BASE(npts) (((npts) + 1) & ~1)
+/* gather mode (gg_tile_gather_kernel): var rows are 64-byte rows fetched by TMA tensor copies in boxes of 16 own rows and
+ * groups of 4 halo rows, so the halo positions start at a multiple of 16 */
+#define CFDP_HALO_BASE_G(npts) (((npts) + 15) & ~15)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -98,6 +101,8 @@ struct ScheduleOptions {
   int refine_rounds;   /* local-search sweeps of the bank placement after the greedy pass (0 = greedy only) */
   int sort_in_tile;    /* 1 = points of a tile in ascending file numbering, 0 = in growth (BFS) order */
   int stage_budget;    /* bytes one tile may occupy in shared memory (blob + var rows + volumes); 0 = no limit */
+  int gather;          /* 1 = schedule for gg_tile_gather_kernel: 64-byte var rows (volume in word 7), halo positions from align16(npts),
+                        * halo rows placed by 16-byte bank group (class = position mod 8, groups = quarter warps) */
 };
 
 /* schedule.cpp */

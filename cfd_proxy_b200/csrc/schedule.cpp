@@ -89,6 +89,9 @@ struct TileBuilder {
   {
     const uint32_t npad = (uint32_t)align_up((size_t)np_, 32);
     nf_ = (int)align_up((size_t)nf_ + 1 + (size_t)opt.slack_slots, 16); nh_ = (int)align_up((size_t)nh_ + (size_t)opt.slack_halo, 16);
+    if (opt.gather)
+      return align_up(std::max(blob_size((uint32_t)nf_, (uint32_t)nh_, (uint32_t)md_, npad), (size_t)CFDP_HALO_BASE(np_) * CFDP_DIM2 * 8), 1024) +
+             (size_t)(CFDP_HALO_BASE_G(np_) + nh_) * 64;
     return align_up(std::max(blob_size((uint32_t)nf_, (uint32_t)nh_, (uint32_t)md_, npad), (size_t)np_ * CFDP_DIM2 * 8), 128) +
            align_up((size_t)(CFDP_HALO_BASE(np_) + nh_) * NGRAD * 8, 128) + align_up((size_t)CFDP_HALO_BASE(np_) * 8, 128);
   }
@@ -222,7 +225,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
    * the sets of rows read together do not change) but lets each point pick the bank-pair class (position mod 16)
    * that collides least with the other rows of the groups it is gathered in.  Halo rows and face slots are placed
    * afterwards against these fixed own rows (pass B). */
-  if (opt.bank_placement) {
+  if (opt.bank_placement && !opt.gather) { /* gather mode: quarter-warp groups, a 16-block permutation would change their membership */
     const int nthr0 = omp_get_max_threads();
     std::vector<std::vector<int>> lmap0((size_t)nthr0);
 #pragma omp parallel
@@ -472,7 +475,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
     out.tile_face_off[(size_t)k + 1] = out.tile_face_off[k] + out.tile_nfaces[k];
     out.tile_halo_off[(size_t)k + 1] = out.tile_halo_off[k] + tnh[k];
     out.max_nfaces = std::max(out.max_nfaces, out.tile_nslots[k]);
-    out.max_nloc = std::max(out.max_nloc, CFDP_HALO_BASE(out.tile_npts[k]) + out.tile_nhpos[k]);
+    out.max_nloc = std::max(out.max_nloc, (opt.gather ? CFDP_HALO_BASE_G(out.tile_npts[k]) : CFDP_HALO_BASE(out.tile_npts[k])) + out.tile_nhpos[k]);
   }
   out.tile_faces = out.tile_face_off[ntiles]; out.halo_refs = out.tile_halo_off[ntiles];
   out.tile_face_ids.resize((size_t)out.tile_faces); out.tile_halo_pts.resize((size_t)out.halo_refs);
@@ -508,7 +511,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
     for (int k = 0; k < ntiles; k++) {
       if (tprof) tb0 = wall();
       const int n = out.tile_npts[k], nf = out.tile_nfaces[k], nh = tnh[k], md = tmaxdeg[k];
-      const int nslots = out.tile_nslots[k], nhpos = out.tile_nhpos[k], n_even = CFDP_HALO_BASE(n);
+      const int nslots = out.tile_nslots[k], nhpos = out.tile_nhpos[k], n_even = opt.gather ? CFDP_HALO_BASE_G(n) : CFDP_HALO_BASE(n); /* first halo position */
       const uint32_t npad = (uint32_t)align_up((size_t)n, 32);
       const int *P = &tb.pts[pt_off[k]];
       unsigned char *bl = &out.blob[out.tile_blob[k]];
@@ -571,7 +574,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
        * are free: greedily give each the class that adds the fewest collisions over the groups it is read in. */
       /* the placement, for an adjacency given as (E_[i*MD + j], D_[i]): nH halo points -> HP (NHP positions), nF faces -> SL (NSL slots) */
       auto place_all = [&](const std::vector<Ent> &E_, const std::vector<int> &D_, int MD, int nH, int nF,
-                           std::vector<int> &HP, int NHP, std::vector<int> &SL, int NSL) {
+                           std::vector<int> &HP, int NHP, std::vector<int> &SL, int NSL, bool rows64, int halo_base) {
       SL.assign((size_t)nF, -1); HP.assign((size_t)nH, -1);
       const int nhw = (n + 15) / 16, ngrp = nhw * MD;
       if (!place_by_bank) {
@@ -721,11 +724,73 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
             pos_of[o] = first + 16 * fillc[cls[o]]++;
           }
         };
-        place(nH, false, cntv, HP, NHP, n_even & 15);
+        /* gather mode: the face walk reads a var row as 16-byte pieces (ld.shared.v2.f64); a quarter warp (8 lanes = 8
+         * consecutive tile points) is conflict free when its rows fall into 8 different 16-byte bank groups, and with the
+         * TMA 64-byte swizzle the group of a piece is a function of (position mod 8) only: class = position mod 8 */
+        auto place_halo8 = [&](std::vector<int> &pos_of, int npos) {
+          const int nq = (n + 7) / 8, ng = nq * MD;
+          std::vector<unsigned char> c8((size_t)ng * 8, 0);
+          for (int q = 0; q < nq; q++)
+            for (int j = 0; j < MD; j++) {
+              unsigned char *cv = &c8[((size_t)q * MD + j) * 8];
+              int seen[8], ns = 0;
+              for (int l = 0; l < 8; l++) {
+                const int i = q * 8 + l;
+                if (i >= n || j >= D_[i]) continue;
+                const int r = E_[(size_t)i * MD + j].nbr;
+                if (r >= n) continue;
+                bool dup = false;
+                for (int t = 0; t < ns; t++) if (seen[t] == r) dup = true;
+                if (!dup) { seen[ns++] = r; cv[r & 7]++; }
+              }
+            }
+          grp_off.assign((size_t)nH + 1, 0);
+          std::vector<int> fill;
+          for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1) { for (int o = 0; o < nH; o++) grp_off[(size_t)o + 1] += grp_off[o]; grp_list.assign((size_t)grp_off[nH], -1); fill.assign(grp_off.begin(), grp_off.end() - 1); }
+            for (int i = 0; i < n; i++)
+              for (int j = 0; j < D_[i]; j++) {
+                const int r = E_[(size_t)i * MD + j].nbr;
+                if (r < n) continue;
+                const int o = r - n, gidx = (i / 8) * MD + j;
+                if (pass == 0) grp_off[(size_t)o + 1]++;
+                else {
+                  bool dup = false;
+                  for (int t = grp_off[o]; t < fill[o]; t++) if (grp_list[t] == gidx) dup = true;
+                  if (!dup) grp_list[fill[o]++] = gidx;
+                }
+              }
+          }
+          const int cap = npos / 8;
+          int used[8] = {0}, fillc[8] = {0};
+          for (int o = 0; o < nH; o++) {
+            int best = -1, best_cost = 1 << 30;
+            for (int c0 = 0; c0 < 8; c0++) {
+              const int c = (c0 + o) & 7;
+              if (used[c] >= cap) continue;
+              int cost = 0;
+              for (int t = grp_off[o]; t < grp_off[(size_t)o + 1]; t++) {
+                const int gi = grp_list[t];
+                if (gi < 0) continue;
+                const unsigned char *cc = &c8[(size_t)gi * 8];
+                int mx = 0;
+                for (int x = 0; x < 8; x++) mx = std::max(mx, (int)cc[x]);
+                if (cc[c] + 1 > mx) cost += 4;
+                cost += cc[c];
+              }
+              if (cost < best_cost) { best_cost = cost; best = c; }
+            }
+            ASSERT(best >= 0);
+            for (int t = grp_off[o]; t < grp_off[(size_t)o + 1]; t++) if (grp_list[t] >= 0) c8[(size_t)grp_list[t] * 8 + best]++;
+            used[best]++;
+            pos_of[o] = best + 8 * fillc[best]++;   /* the first halo position is a multiple of 16 */
+          }
+        };
+        if (rows64) place_halo8(HP, NHP); else place(nH, false, cntv, HP, NHP, halo_base & 15);
         place(nF, true, cntn, SL, NSL, 0);
       }
       };
-      place_all(tile_ents, deg, md, nh, nf, hpos_of, nhpos, slot_of, nslots);
+      place_all(tile_ents, deg, md, nh, nf, hpos_of, nhpos, slot_of, nslots, opt.gather != 0, n_even);
       TB(1);
 
       /* ---- emit */
@@ -787,7 +852,8 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
           }
         }
         const int nfslots = (int)align_up((size_t)nff, 16), nfhpos = (int)align_up((size_t)nfh, 16);
-        place_all(ftile_ents, fdeg, std::max(fmd, 1), nfh, nff, fhpos_of, nfhpos, fslot_of, nfslots);
+        const int fbase = CFDP_HALO_BASE(n);   /* the pseudo-flux kernel keeps 72-byte rows: its own halo base and 16 classes */
+        place_all(ftile_ents, fdeg, std::max(fmd, 1), nfh, nff, fhpos_of, nfhpos, fslot_of, nfslots, false, fbase);
         std::vector<unsigned char> &fb = ftile_bytes[k];
         fb.assign(blob_size((uint32_t)nfslots, (uint32_t)nfhpos, (uint32_t)fmd, npad), 0);
         double *fn = (double *)fb.data();
@@ -806,7 +872,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
         for (int i = 0; i < n; i++)
           for (int c = 0; c < fdeg[i]; c++) {
             const Ent &e = ftile_ents[(size_t)i * fmd + c];
-            const uint32_t loc = e.nbr < n ? (uint32_t)e.nbr : (uint32_t)(n_even + fhpos_of[e.nbr - n]);
+            const uint32_t loc = e.nbr < n ? (uint32_t)e.nbr : (uint32_t)(fbase + fhpos_of[e.nbr - n]);
             fe[(size_t)c * npad + i] = loc | (fghost[(size_t)i * fmd + c] ? 0x8000u : 0u) | ((uint32_t)fslot_of[e.fid] << 16) | (e.sign << 31);
           }
         out.ftile_nfaces[k] = nfslots; out.ftile_nhalo[k] = nfhpos; out.ftile_maxdeg[k] = fmd;

@@ -133,7 +133,7 @@ struct Engine {
   unsigned char *d_blob = nullptr;
   TileDesc *d_tiles = nullptr;
   size_t blob_bytes = 0;
-  int smem_bytes = 0, region0_doubles = 0, block_threads = 0;
+  int smem_bytes = 0, region0_doubles = 0, block_threads = 0, ctas_per_sm = 2, var_refresh = 0;
   int kernel_version = 2, chunk = 16, smem_v1 = 0, persistent = 0; ggk::PipeLayout pipe = {}; ggk4::PipeLayout pipe4 = {}; uint32_t max_hvpv = 0;
   unsigned long long *d_progress = nullptr; unsigned long long progress_target = 0; int fused_signal = 1;
   /* fused pack: per boundary tile, the rows other domains need (export lists), written by the gradient kernel itself */
@@ -475,10 +475,12 @@ static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st, 
       grid = (unsigned)((ntiles + E.chunk - 1) / E.chunk);
       P.cstride = E.chunk; P.istride = 1; P.maxcount = E.chunk;
     }
-    if (E.exact)
-      ggk::gg_tile_pipe_kernel<true><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.d_blob, E.d_var, E.d_hhalo, E.d_pvol, E.d_grad, P);
-    else
-      ggk::gg_tile_pipe_kernel<false><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.d_blob, E.d_var, E.d_hhalo, E.d_pvol, E.d_grad, P);
+    P.variant = env_int("CFDP_VARIANT", 1); /* 1 = L2 prefetch of the next tile's late-fetched blob head (+5.5 .. 7 %, profiles/README.md) */
+#define CFDP_LAUNCH_PIPE(EX, NC) ggk::gg_tile_pipe_kernel<EX, NC><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.d_blob, E.d_var, E.d_hhalo, E.d_pvol, E.d_grad, P)
+    if (E.ctas_per_sm == 4) { if (E.exact) CFDP_LAUNCH_PIPE(true, 4); else CFDP_LAUNCH_PIPE(false, 4); }
+    else if (E.ctas_per_sm == 3) { if (E.exact) CFDP_LAUNCH_PIPE(true, 3); else CFDP_LAUNCH_PIPE(false, 3); }
+    else { if (E.exact) CFDP_LAUNCH_PIPE(true, 2); else CFDP_LAUNCH_PIPE(false, 2); }
+#undef CFDP_LAUNCH_PIPE
   } else if (E.kernel_version == 3) { /* round-1 production kernel, kept for side-by-side timing (no fused pack) */
     E.pipe4.nsignal = nsignal; E.pipe4.progress = E.d_progress; E.pipe4.tile_base = (int)tile0; E.pipe4.nexport = 0; E.pipe4.exp_off = E.d_exp_off; E.pipe4.exp_src = E.d_exp_src; E.pipe4.exp_dst = E.d_exp_dst; E.pipe4.sendbuf = E.d_sendbuf;
     const int chunk = std::min(E.chunk, CFDP_MAX_CHUNK_V4);
@@ -522,10 +524,11 @@ static void launch_flux(long long tile0, long long ntiles, cudaStream_t st)
   if (version == 2 && E.max_nhalo <= CFDP_FLUX_HALO_PER_THREAD * E.block_threads) {
     const int chunk = std::min(E.chunk, CFDP_FLUX_MAX_CHUNK);
     const unsigned grid = (unsigned)((ntiles + chunk - 1) / chunk);
+    const int fvariant = env_int("CFDP_FLUX_VARIANT", 2); /* 2 = the next tile's grad rows are asked into L2 before this tile's walk (+3 %) */
     if (E.exact)
-      ggk::psd_flux_pipe_kernel<true><<<grid, E.block_threads, E.flux_smem, st>>>(tiles + tile0, (int)ntiles, chunk, blob, E.d_grad, E.d_flux);
+      ggk::psd_flux_pipe_kernel<true><<<grid, E.block_threads, E.flux_smem, st>>>(tiles + tile0, (int)ntiles, chunk, blob, E.d_grad, E.d_flux, fvariant);
     else
-      ggk::psd_flux_pipe_kernel<false><<<grid, E.block_threads, E.flux_smem, st>>>(tiles + tile0, (int)ntiles, chunk, blob, E.d_grad, E.d_flux);
+      ggk::psd_flux_pipe_kernel<false><<<grid, E.block_threads, E.flux_smem, st>>>(tiles + tile0, (int)ntiles, chunk, blob, E.d_grad, E.d_flux, fvariant);
   } else if (E.exact)
     ggk::psd_flux_tile_kernel<true><<<(unsigned)ntiles, E.block_threads, E.flux_smem, st>>>(tiles + tile0, blob, E.d_grad, E.d_flux);
   else
@@ -742,8 +745,8 @@ static void configure_kernel(int version, int chunk, int persistent)
 {
   Engine &E = g_eng;
   /* pipelined kernels: one stage [blob | var rows | volumes] per CTA, two CTAs per SM.  The production kernel keeps the
-   * var rows at the END of the stage: they must never overlap the rows the previous tile is still storing (8 zones) */
-  E.pipe.stage_bytes = std::max(E.max_footprint, (uint32_t)(8 * CFDP_ZONE_BYTES) + E.max_hvpv);
+   * var rows at the END of the stage: they must never overlap the rows the previous tile is still storing (one zone per warp) */
+  E.pipe.stage_bytes = std::max(E.max_footprint, (uint32_t)((E.block_threads / 32) * CFDP_ZONE_BYTES) + E.max_hvpv);
   E.pipe4.stage_bytes = E.max_footprint;
   E.kernel_version = version;
   E.chunk = std::max(1, chunk);
@@ -761,8 +764,19 @@ static void configure_kernel(int version, int chunk, int persistent)
   CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
   CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
   if (E.kernel_version == 2) {
-    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
-    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    /* CFDP_CTAS = 3 / 4: three CTAs of <= 160 threads (15 warps, <= 75 KB each) or four of <= 128 (16 warps, <= 56 KB) per SM
+     * instead of two of 256; the register file holds 128 registers per thread in all three shapes */
+    const int want = env_int("CFDP_CTAS", 2);
+    E.ctas_per_sm = (want == 4 && E.block_threads <= 128 && E.smem_bytes <= 56 * 1024) ? 4 : (want == 3 && E.block_threads <= 160 && E.smem_bytes <= 75 * 1024) ? 3 : 2;
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    if (E.ctas_per_sm == 3) {
+      CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+      CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    } else if (E.ctas_per_sm == 4) {
+      CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+      CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
+    }
   } else if (E.kernel_version == 3) {
     CUDA_CHECK(cudaFuncSetAttribute(ggk4::gg_tile_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
     CUDA_CHECK(cudaFuncSetAttribute(ggk4::gg_tile_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
@@ -1278,6 +1292,7 @@ extern "C" double cfdp_iterate(int variant, int niter, int final_last)
   if (env_int("CFDP_TIMELINE", 0) && variant != CFDP_COMM_FREE) timeline_probe(variant);
   CUDA_CHECK(cudaEventRecord(E.ev_t0, E.s_comp));
   for (int i = 0; i < niter; i++) {
+    if (E.var_refresh) launch_halo_pack(0, E.ntiles, E.s_comp);
     run_iteration(variant);
     if (E.with_flux) launch_flux(0, E.ntiles, E.s_comp); /* solver.c:45-55: gradient (+ exchange), then the pseudo flux; s_comp has joined the exchange */
   }
@@ -1290,6 +1305,21 @@ extern "C" double cfdp_iterate(int variant, int niter, int final_last)
 }
 
 extern "C" void cfdp_set_flux(int on) { g_eng.with_flux = on ? 1 : 0; }
+extern "C" void cfdp_set_var_refresh(int on) { g_eng.var_refresh = on ? 1 : 0; }
+
+/* rebuild the packed halo rows of every tile from the device var rows (var was changed on the device); device time in ms */
+extern "C" double cfdp_refresh_var(int niter)
+{
+  Engine &E = g_eng;
+  cfdp_commit();
+  CUDA_CHECK(cudaEventRecord(E.ev_t0, E.s_comp));
+  for (int i = 0; i < niter; i++) launch_halo_pack(0, E.ntiles, E.s_comp);
+  CUDA_CHECK(cudaEventRecord(E.ev_t1, E.s_comp));
+  CUDA_CHECK(cudaEventSynchronize(E.ev_t1));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, E.ev_t0, E.ev_t1));
+  return (double)ms;
+}
 
 /* niter pseudo-flux passes over all hosted domains on the device grad as it stands; returns the device time in ms */
 extern "C" double cfdp_flux_iterate(int niter)

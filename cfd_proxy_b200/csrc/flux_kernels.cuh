@@ -157,6 +157,8 @@ __device__ __forceinline__ void flux_row_piece(double *sdst, const double *gsrc,
   }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 #define CFDP_FLUX_HALO_PER_THREAD 4 /* halo rows a thread gathers: nhalo <= 4 * blockDim */
 #define CFDP_FLUX_MAX_CHUNK 16       /* tiles per CTA (descriptors in static shared memory: every byte counts against two CTAs per SM) */
 
@@ -171,7 +173,7 @@ __device__ __forceinline__ void flux_row_piece(double *sdst, const double *gsrc,
 template <bool EXACT>
 __global__ void __launch_bounds__(CFDP_MAX_TILE_POINTS, 2)
 psd_flux_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, const unsigned char *__restrict__ blob,
-                     const double *__restrict__ grad, double *__restrict__ flux)
+                     const double *__restrict__ grad, double *__restrict__ flux, int variant)
 {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full;
@@ -248,6 +250,30 @@ psd_flux_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, int chunk, 
     cp_async_wait_all();
     __syncthreads();                       /* everybody's rows have landed */
     mbar_wait(&full, (uint32_t)it & 1u);   /* normals and adjacency have landed */
+
+    if (variant && t + 1 < t_end) {
+      /* everything the next tile reads is asked into L2 before this tile's walk: its loads, issued after the walk and
+       * waited for at once, then cost an L2 round trip instead of a DRAM one.  1 = blob, 2 = grad rows, 3 = both */
+      const TileDesc pd = s_tds[t + 1 - t_begin];
+      if ((variant & 1) && tid == 0) {
+        const unsigned char *nb = blob + pd.blob_off();
+        const uint32_t a_src = flux_adj_src(pd.halo_off, pd.nhalo);
+        if (pd.halo_off) bulk_prefetch_l2(nb, (pd.halo_off + 15u) & ~15u);
+        if (pd.blob_bytes > a_src) bulk_prefetch_l2(nb + a_src, (pd.blob_bytes - a_src + 15u) & ~15u);
+      }
+      if (variant & 2) {
+        if (tid < (int)pd.npts) {
+          const char *g = reinterpret_cast<const char *>(grad + (size_t)(pd.row0 + tid) * (NGRAD * 3));
+          prefetch_l2(g); prefetch_l2(g + 64);
+        }
+#pragma unroll
+        for (int k = 0; k < CFDP_FLUX_HALO_PER_THREAD; k++)
+          if (hrow[k] != 0xFFFFFFFFu) {
+            const char *g = reinterpret_cast<const char *>(grad + (size_t)hrow[k] * (NGRAD * 3));
+            prefetch_l2(g); prefetch_l2(g + 64);
+          }
+      }
+    }
 
     if (tid < npts) {
       const double *s_nrm = reinterpret_cast<const double *>(smem);

@@ -191,6 +191,9 @@ struct PipeLayout {
   unsigned long long *prof;        /* optional: SM cycles of thread 0 summed over tiles: [0] wait for data, [1] face walk, [2] rest, [4] tiles */
   unsigned long long *progress;    /* counts finished boundary tiles (tile index < nsignal): the early-send trigger the comm stream waits on */
   int nsignal;
+  int variant;                     /* experiment switches (CFDP_VARIANT): 1 = L2 prefetch of the next tile's late-fetched blob head at the start of
+                                    * the face walk, 2 = of all of the next tile, 4 = issued by the last warp instead of warp 0,
+                                    * 8 = early fetch after warp 0's store, 16 = prefetch the whole blob, 32 = early fetch issued by four warps */
   int tile_base;                   /* global index of this launch's first tile */
   int nexport;                     /* global tiles [0, nexport) write their export rows (fused pack / direct halo stores); 0 = off */
   const uint32_t *exp_off, *exp_src, *exp_dst; /* per boundary tile: (tile-local point | destination array << 16) -> row of that array */
@@ -229,6 +232,10 @@ __device__ __forceinline__ void bulk_g2s_a(uint32_t sdst, const void *src, uint3
 {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                ::"r"(sdst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async8_a(uint32_t sdst, const void *src)
 {
@@ -309,8 +316,8 @@ halo_pack_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsigned 
  *        stores into the ghost rows of a peer GPU) between two barriers, and bump the arrival counters.
  * No thread ever touches global memory with a load: HBM is read by TMA bulk copies only.
  */
-template <bool EXACT>
-__global__ void __launch_bounds__(CFDP_MAX_TILE_POINTS, 2)
+template <bool EXACT, int CTAS>
+__global__ void __launch_bounds__(CTAS == 4 ? 128 : CTAS == 3 ? 160 : CFDP_MAX_TILE_POINTS, CTAS)
 gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsigned char *__restrict__ blob,
                     const double *__restrict__ hvar, const double *__restrict__ hhalo, const double *__restrict__ pvol,
                     double *__restrict__ grad, PipeLayout L)
@@ -320,6 +327,8 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
   __shared__ __align__(16) TileDesc s_desc[4];                  /* ring: descriptors of tiles i, i+1, i+2 of this CTA */
   __shared__ uint32_t s_eoff[4][2];                              /* ring: export list bounds of those tiles */
   __shared__ uint32_t s_exp[2 * CFDP_MAX_EXPORT];                /* this tile's export list: sources, then destinations */
+  __shared__ uint32_t s_soff[4][2];                              /* ring: bounds of those tiles' peer-signal entries (direct halo stores) */
+  __shared__ uint32_t s_sig[CFDP_EXP_BASES - 2];                 /* this tile's peer-signal entries */
   __shared__ unsigned long long s_sigacc[CFDP_EXP_BASES - 2];    /* rows stored into each peer's memory and not yet signalled (thread 0 only) */
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   /* this CTA's tiles: t(i) = first + i*istride, i < count */
@@ -339,6 +348,9 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
       else if (tid < 10) {
         const int gt = L.tile_base + t + (tid - 8);
         if (gt <= L.nexport && L.nexport > 0) cp_async4(&s_eoff[i & 3][tid - 8], L.exp_off + gt); /* exp_off has nexport + 1 entries */
+      } else if (tid < 12) {
+        const int gt = L.tile_base + t + (tid - 10);
+        if (gt <= L.nexport && L.nexport > 0 && L.sig_off) cp_async4(&s_soff[i & 3][tid - 10], L.sig_off + gt);
       }
     }
   };
@@ -396,6 +408,9 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
     const uint32_t e0 = gt < L.nexport ? s_eoff[i & 3][0] : 0u;
     const int nexp = gt < L.nexport ? (int)(s_eoff[i & 3][1] - e0) : 0;
     const bool exp_in_smem = nexp > 0 && nexp <= CFDP_MAX_EXPORT;
+    const uint32_t g0 = (nexp > 0 && L.sig_off) ? s_soff[i & 3][0] : 0u;
+    const int nsig = (nexp > 0 && L.sig_off) ? (int)(s_soff[i & 3][1] - g0) : 0;   /* <= one entry per peer */
+    if (tid >= 32 && tid < 32 + nsig) cp_async4(&s_sig[tid - 32], L.sig_ent + g0 + (tid - 32));
     if (exp_in_smem) {
       for (int k = tid; k < nexp; k += nthr) {
         cp_async4(&s_exp[k], L.exp_src + e0 + k);
@@ -403,6 +418,27 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
       }
     }
     cp_async_commit();
+    if (L.variant & 3) {
+      /* the next tile's bytes are asked into L2 now, so that its bulk copies (issued once this tile's walk is over, the
+       * blob head only after the result rows have left) find them there instead of paying a DRAM round trip */
+      const int pw = (L.variant & 4) ? (nthr >> 5) - 1 : 0;
+      if (has_next && warp == pw && lane == 0) {
+        const TileDesc &pd = s_desc[(i + 1) & 3];
+        const unsigned char *src = blob + pd.blob_off();
+        const uint32_t oc = CFDP_HALO_BASE((uint32_t)npts) * CFDP_ROW_BYTES;
+        if (L.variant & 2) {
+          const uint32_t ne = CFDP_HALO_BASE((uint32_t)pd.npts);
+          bulk_prefetch_l2(src, (pd.blob_bytes + 15u) & ~15u);
+          bulk_prefetch_l2(hvar + (size_t)pd.row0 * NGRAD, ne * (NGRAD * 8));
+          if (pd.nhalo) bulk_prefetch_l2(hhalo + (size_t)pd.hrow0 * NGRAD, (uint32_t)pd.nhalo * (NGRAD * 8));
+          bulk_prefetch_l2(pvol + pd.row0, ne * 8);
+        } else if (L.variant & 16) {
+          bulk_prefetch_l2(src, (pd.blob_bytes + 15u) & ~15u);
+        } else {
+          bulk_prefetch_l2(src, ((oc < pd.blob_bytes ? oc : pd.blob_bytes) + 15u) & ~15u);
+        }
+      }
+    }
 
     double acc[NGRAD * 3];
 #pragma unroll
@@ -449,7 +485,22 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
     TileDesc nd = td;
     if (has_next) { /* early fetch of the next tile: runs under the staging / store of this one */
       nd = s_desc[(i + 1) & 3];
-      if (tid == 0) bulk_early(nd, out_cover < nd.blob_bytes ? out_cover : nd.blob_bytes);
+      if (L.variant & 32) {
+        /* the four requests leave from four warps: the warp that issues them all reaches its own store (and the late
+         * fetch of its zone, the last bytes the next tile waits for) about a thousand cycles after the others */
+        const int nwp = nthr >> 5;
+        const uint32_t ne = CFDP_HALO_BASE((uint32_t)nd.npts);
+        const uint32_t nv = ne * (NGRAD * 8), nh = (uint32_t)nd.nhalo * (NGRAD * 8), np = ne * 8;
+        const uint32_t a_hv = sbase + stage_hvar_off(L.stage_bytes, nd.npts, nd.nhalo);
+        if (tid == 0) {
+          const uint32_t hole = ((uint32_t)nd.nhalo * 4u + 15u) & ~15u;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nd.blob_bytes - hole + nv + nh + np) : "memory");
+          blob_fetch(nd, out_cover < nd.blob_bytes ? out_cover : nd.blob_bytes, nd.blob_bytes);
+        }
+        if (tid == 32 * min(1, nwp - 1)) bulk_g2s_a(a_hv, hvar + (size_t)nd.row0 * NGRAD, nv, bar, pol_stream);
+        if (tid == 32 * min(2, nwp - 1) && nh) bulk_g2s_a(a_hv + nv, hhalo + (size_t)nd.hrow0 * NGRAD, nh, bar, pol_stream);
+        if (tid == 32 * min(3, nwp - 1)) bulk_g2s_a(sbase + stage_pvol_off(L.stage_bytes, nd.npts), pvol + nd.row0, np, bar, pol_stream);
+      } else if (tid == 0 && !(L.variant & 8)) bulk_early(nd, out_cover < nd.blob_bytes ? out_cover : nd.blob_bytes);
     }
     long long q1 = 0, q2 = 0, q3 = 0;
     if (L.prof && tid == 0) q1 = clock64();
@@ -467,6 +518,8 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
       if (lane == 0) {
         bulk_s2g(grad + ((size_t)td.row0 + 32u * warp) * (NGRAD * 3), sbase + CFDP_ZONE_BYTES * (uint32_t)warp, rows_w * CFDP_ROW_BYTES, pol_stream);
         bulk_commit();
+        /* variant 8: thread 0 requests the next tile only now, while the store engine reads its zone */
+        if (tid == 0 && has_next && (L.variant & 8)) bulk_early(nd, out_cover < nd.blob_bytes ? out_cover : nd.blob_bytes);
       }
     }
     if (L.prof && tid == 0) q2 = clock64();
@@ -477,21 +530,28 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
        * warp export the rows of its own zone without the two barriers measured slower: 5.4 % against 1.7 % of a
        * 16.8 M-point iteration.) */
       __syncthreads();
-      const double *s_out = reinterpret_cast<const double *>(smem);
-      const int nw = nexp * (NGRAD * 3);
+      /* a 168-byte row leaves as ten 16-byte stores and one 8-byte store (at its head when the destination row is odd:
+       * rows are 8-byte aligned, every second one 16-byte aligned); one store per thread and step */
+      const int nw = nexp * 11;
       for (int k = tid; k < nw; k += nthr) {
-        const int r = k / (NGRAD * 3), c = k - r * (NGRAD * 3);
+        const int r = k / 11, c = k - r * 11;
         const uint32_t sk = exp_in_smem ? s_exp[r] : __ldg(L.exp_src + e0 + r);     /* tile-local point | destination array << 16 */
         const uint32_t dst = exp_in_smem ? s_exp[CFDP_MAX_EXPORT + r] : __ldg(L.exp_dst + e0 + r);
-        L.exp_base[sk >> 16][(size_t)dst * (NGRAD * 3) + c] = s_out[(sk & 0xFFFFu) * (NGRAD * 3) + c];
-      }
-      __syncthreads(); /* the staged rows have been read by every thread; the stores are ordered before thread 0's releases */
-      if (tid == 0 && L.sig_off) { /* rows this tile stores into peer memory: signalled in one go per CTA, below */
-        for (uint32_t s = __ldg(L.sig_off + gt), s1 = __ldg(L.sig_off + gt + 1); s < s1; s++) {
-          const uint32_t ent = __ldg(L.sig_ent + s);
-          s_sigacc[ent & 15u] += (unsigned long long)(ent >> 4);
+        double *g = L.exp_base[sk >> 16] + (size_t)dst * (NGRAD * 3);
+        const uint32_t a = sbase + CFDP_ROW_BYTES * (sk & 0xFFFFu);
+        const uint32_t odd = dst & 1u;
+        if (c == 10) {        /* the 8-byte piece: word 0 of an odd row, word 20 of an even one */
+          const uint32_t w = odd ? 0u : 20u;
+          g[w] = lds_f64(a + 8u * w);
+        } else {
+          const uint32_t w = 2u * (uint32_t)c + odd;
+          const double2 v = make_double2(lds_f64(a + 8u * w), lds_f64(a + 8u * w + 8u));
+          *reinterpret_cast<double2 *>(g + w) = v;
         }
       }
+      __syncthreads(); /* the staged rows have been read by every thread; the stores are ordered before thread 0's releases */
+      if (tid == 0) /* rows this tile stores into peer memory: signalled in one go per CTA, below */
+        for (int q = 0; q < nsig; q++) s_sigacc[s_sig[q] & 15u] += (unsigned long long)(s_sig[q] >> 4);
     }
     if (rows_w && lane == 0) {
       bulk_wait_read();      /* the zone may be overwritten: late fetch of the next tile's bytes that live in it */

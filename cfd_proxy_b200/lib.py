@@ -122,7 +122,7 @@ EXPORTED = [
     "compute_gradients_gg_gaspi_bulk_sync", "compute_gradients_gg_gaspi_async",
     "compute_gradients_gg_mpifence_bulk_sync", "compute_gradients_gg_mpifence_async",
     "compute_gradients_gg_mpipscw_bulk_sync", "compute_gradients_gg_mpipscw_async",
-    "exchange_dbl_mpi_post_recv", "compute_psd_flux", "cfdp_grad_to_device", "cfdp_flux_to_host", "cfdp_set_flux", "cfdp_flux_iterate",
+    "exchange_dbl_mpi_post_recv", "compute_psd_flux", "cfdp_grad_to_device", "cfdp_flux_to_host", "cfdp_set_flux", "cfdp_flux_iterate", "cfdp_refresh_var", "cfdp_set_var_refresh",
     "get_nc_val", "get_nc_int", "get_nc_double",
     "cfdp_nc_open", "cfdp_nc_close", "cfdp_nc_strerror", "cfdp_nc_inq_dimid", "cfdp_nc_inq_dimlen",
     "cfdp_nc_inq_varid", "cfdp_nc_get_var_int", "cfdp_nc_get_var_double",
@@ -170,6 +170,8 @@ def load() -> C.CDLL:
     sig("cfdp_flux_to_host", None, sd_p)
     sig("cfdp_set_flux", None, C.c_int)
     sig("cfdp_flux_iterate", C.c_double, C.c_int)
+    sig("cfdp_refresh_var", C.c_double, C.c_int)
+    sig("cfdp_set_var_refresh", None, C.c_int)
     sig("get_nc_val", C.c_int, C.c_int, C.c_char_p)
     sig("get_nc_int", None, C.c_int, C.c_char_p, c_int_p)
     sig("get_nc_double", None, C.c_int, C.c_char_p, c_dbl_p)

@@ -209,6 +209,12 @@ int cfdp_get_phase_profile(unsigned long long *out8, int reset);
 /* run `niter` iterations of variant over ALL hosted domains, device resident; returns the
  * device time in milliseconds (CUDA events on the compute stream) */
 double cfdp_iterate(int variant, int niter, int final_last);
+/* A solver that keeps var on the device and changes it there (the reference only ever reads sd->var, solver.c:45-55) tells
+ * the library so: the derived per-tile copies of the halo var rows are rebuilt from the device var rows.
+ * cfdp_refresh_var(niter) does that niter times and returns the device time in ms; cfdp_set_var_refresh(1) makes every
+ * iteration of cfdp_iterate start with it (the cost model "var is new in every iteration", bench.py `var_refresh`). */
+double cfdp_refresh_var(int niter);
+void cfdp_set_var_refresh(int on);
 /* on = 1: every iteration of cfdp_iterate also runs the pseudo flux after the exchange (solver.c:45-55) */
 void cfdp_set_flux(int on);
 /* `niter` pseudo-flux passes over all hosted domains on the device grad as it stands; device time in ms */

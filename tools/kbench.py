@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel-only sweep (comm_free iterations) over schedule / kernel configurations.
 usage: python tools/kbench.py [--mpoints 16] [--f6likeN] [--iters K] mesh ...
-  mesh = tile:order:fma/kcfg,kcfg,...   kcfg = version.chunk.persistent   e.g. 256:lex:0/2.8.0,3.8.0,2.1.296
+  mesh = tile:order:fma[:stage budget[:CTAs per SM]]/kcfg,kcfg,...   kcfg = version.chunk.persistent[.variant]   e.g. 256:lex:0/2.8.0,3.8.0,2.1.296
 The mesh and its schedule are built once per `mesh`; the kernel configurations are switched on the live session."""
 import ctypes as C, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,7 +23,8 @@ def main():
     peak, _ = measured_peak()
     for mesh in args:
         head, kcfgs = mesh.split("/")
-        tile, order, fma, budget = (head.split(":") + ["0"])[:4]
+        tile, order, fma, budget, ctas = (head.split(":") + ["0", "2"])[:5]
+        os.environ["CFDP_CTAS"] = ctas
         if int(budget):
             os.environ["CFDP_STAGE_BUDGET"] = budget
         else:
@@ -68,12 +69,21 @@ def main():
                 print(json.dumps(dict(mesh=head, kernel=kc, kernel_ms=round(ms, 4), spread=[round(min(r["k"]), 4), round(max(r["k"]), 4)], gfaces=round(st.nfaces / ms / 1e6, 2), frac=round(st.alg_bytes / ms / 1e6 / peak, 4),
                                       async_ms=round(ms_a, 4), bulk_ms=round(ms_b, 4), boundary_tiles=st.nboundary_tiles, smem=st.smem_bytes, tiles=st.ntiles, dup=round(st.tile_faces / st.nfaces, 3),
                                       blob_B_per_face=round(st.blob_bytes / st.nfaces, 2), setup_s=round(setup_s, 1), phase=prof)), flush=True)
-            if os.environ.get("KBENCH_FLUX"):
+            if os.environ.get("KBENCH_FLUX"):   # KBENCH_FLUX=0,1,2,3: pseudo-flux kernel variants (CFDP_FLUX_VARIANT), interleaved
+                fv = os.environ["KBENCH_FLUX"].split(",")
                 S.flux_iterate(3)
-                ms_f = S.flux_iterate(iters) / iters
+                fr = {v: [] for v in fv}
+                for rnd in range(rounds):
+                    for v in fv:
+                        os.environ["CFDP_FLUX_VARIANT"] = v
+                        S.flux_iterate(2)
+                        fr[v].append(S.flux_iterate(iters) / iters)
                 st = S.stats()
-                print(json.dumps(dict(mesh=head, flux_ms=round(ms_f, 4), flux_frac=round(st.flux_alg_bytes / ms_f / 1e6 / peak, 4), flux_smem=st.flux_smem_bytes,
-                                      flux_blob_B_per_face=round(st.flux_blob_bytes / st.nfaces, 2))), flush=True)
+                for v in fv:
+                    ms_f = sorted(fr[v])[len(fr[v]) // 2]
+                    print(json.dumps(dict(mesh=head, flux_variant=v, flux_ms=round(ms_f, 4), spread=[round(min(fr[v]), 4), round(max(fr[v]), 4)],
+                                          flux_frac=round(st.flux_alg_bytes / ms_f / 1e6 / peak, 4), flux_smem=st.flux_smem_bytes,
+                                          flux_blob_B_per_face=round(st.flux_blob_bytes / st.nfaces, 2))), flush=True)
 
 if __name__ == "__main__":
     main()

@@ -35,7 +35,6 @@
 #include <omp.h>
 #include "common.h"
 #include "gg_kernels.cuh"
-#include "gg_kernels_v4.cuh"
 #include "flux_kernels.cuh"
 
 #define CUDA_CHECK(call)                                                                           \
@@ -134,7 +133,7 @@ struct Engine {
   TileDesc *d_tiles = nullptr;
   size_t blob_bytes = 0;
   int smem_bytes = 0, region0_doubles = 0, block_threads = 0, ctas_per_sm = 2, var_refresh = 0;
-  int kernel_version = 2, chunk = 16, smem_v1 = 0, persistent = 0; ggk::PipeLayout pipe = {}; ggk4::PipeLayout pipe4 = {}; uint32_t max_hvpv = 0;
+  int kernel_version = 2, chunk = 16, smem_v1 = 0, persistent = 0; ggk::PipeLayout pipe = {}; uint32_t max_hvpv = 0;
   unsigned long long *d_progress = nullptr; unsigned long long progress_target = 0; int fused_signal = 1;
   /* fused pack: per boundary tile, the rows other domains need (export lists), written by the gradient kernel itself */
   std::vector<uint32_t> h_exp_off, h_exp_src, h_exp_dst; uint32_t *d_exp_off = nullptr, *d_exp_src = nullptr, *d_exp_dst = nullptr; int fused_pack = 1;
@@ -249,12 +248,6 @@ extern "C" int cfdp_configure(int proc_rank, int nprocs, int ndomains_total, int
   E.sopt.tile_points = env_int("CFDP_TILE_POINTS", 256);
   E.sopt.max_faces = env_int("CFDP_TILE_MAX_FACES", 2688);
   E.sopt.max_local = env_int("CFDP_TILE_MAX_LOCAL", 768);
-  {
-    /* threads that gather halo rows (gg_tile_pipe_kernel): all of the block, minus warp 0 for blocks of >= 128 threads */
-    const int blk = (int)align_up((size_t)E.sopt.tile_points, 32), gth = blk >= 128 ? blk - 32 : blk;
-    const int max_halo = gth * CFDP_MAX_GATHER_PER_THREAD / NGRAD;
-    E.sopt.max_local = std::min(E.sopt.max_local, E.sopt.tile_points + max_halo);
-  }
   E.sopt.order = env_int("CFDP_TILE_ORDER", 0);
   E.sopt.sort_in_tile = env_int("CFDP_SORT_IN_TILE", 1);
   E.sopt.flux_blob = env_int("CFDP_FLUX_BLOB", 1);
@@ -475,20 +468,20 @@ static void launch_gradient(long long tile0, long long ntiles, cudaStream_t st, 
       grid = (unsigned)((ntiles + E.chunk - 1) / E.chunk);
       P.cstride = E.chunk; P.istride = 1; P.maxcount = E.chunk;
     }
+    /* direct halo stores: boundary tiles dealt out over the first CFDP_DIRECT_SPREAD percent of the walk (default 0 = boundary tiles
+     * first; spreading measured SLOWER at 2 GPUs: every CTA then pays one system-scope release, profiles/README.md) */
+    P.spread_m = 0; P.spread_nb = 0;
+    if (direct && tile0 == 0 && ntiles == E.ntiles && E.nbtiles > 0) {
+      const long long pct = env_int("CFDP_DIRECT_SPREAD", 0);
+      const long long m = E.ntiles * pct / 100 / E.nbtiles;
+      if (m > 1) { P.spread_m = (int)m; P.spread_nb = (int)E.nbtiles; }
+    }
     P.variant = env_int("CFDP_VARIANT", 1); /* 1 = L2 prefetch of the next tile's late-fetched blob head (+5.5 .. 7 %, profiles/README.md) */
 #define CFDP_LAUNCH_PIPE(EX, NC) ggk::gg_tile_pipe_kernel<EX, NC><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, E.d_blob, E.d_var, E.d_hhalo, E.d_pvol, E.d_grad, P)
     if (E.ctas_per_sm == 4) { if (E.exact) CFDP_LAUNCH_PIPE(true, 4); else CFDP_LAUNCH_PIPE(false, 4); }
     else if (E.ctas_per_sm == 3) { if (E.exact) CFDP_LAUNCH_PIPE(true, 3); else CFDP_LAUNCH_PIPE(false, 3); }
     else { if (E.exact) CFDP_LAUNCH_PIPE(true, 2); else CFDP_LAUNCH_PIPE(false, 2); }
 #undef CFDP_LAUNCH_PIPE
-  } else if (E.kernel_version == 3) { /* round-1 production kernel, kept for side-by-side timing (no fused pack) */
-    E.pipe4.nsignal = nsignal; E.pipe4.progress = E.d_progress; E.pipe4.tile_base = (int)tile0; E.pipe4.nexport = 0; E.pipe4.exp_off = E.d_exp_off; E.pipe4.exp_src = E.d_exp_src; E.pipe4.exp_dst = E.d_exp_dst; E.pipe4.sendbuf = E.d_sendbuf;
-    const int chunk = std::min(E.chunk, CFDP_MAX_CHUNK_V4);
-    const unsigned grid = (unsigned)((ntiles + chunk - 1) / chunk);
-    if (E.exact)
-      ggk4::gg_tile_pipe_kernel<true><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, chunk, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.pipe4);
-    else
-      ggk4::gg_tile_pipe_kernel<false><<<grid, E.block_threads, E.smem_bytes, st>>>(E.d_tiles + tile0, (int)ntiles, chunk, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.pipe4);
   } else {
     if (E.exact)
       ggk::gg_tile_kernel<true><<<(unsigned)ntiles, E.block_threads, E.smem_v1, st>>>(E.d_tiles + tile0, E.d_blob, E.d_var, E.d_pvol, E.d_grad, E.region0_doubles);
@@ -698,6 +691,9 @@ extern "C" void cfdp_plan(void)
     for (const Seg &sg : ss) E.h_send_rows.insert(E.h_send_rows.end(), sg.rows->begin(), sg.rows->end());
     for (const Seg &sg : rs) E.h_recv_rows.insert(E.h_recv_rows.end(), sg.rows->begin(), sg.rows->end());
     pp.send_rows = (long long)E.h_send_rows.size() - pp.send_off; pp.recv_rows = (long long)E.h_recv_rows.size() - pp.recv_off;
+    /* halo relations are symmetric (a face joins a point of each side): the stage-parity double buffering of the put + notify
+     * window relies on it -- a peer that only received could be overrun by a sender two stages ahead */
+    ASSERT((pp.send_rows > 0) == (pp.recv_rows > 0));
     E.peers.push_back(pp);
   }
   E.n_send = (long long)E.h_send_rows.size(); E.n_recv = (long long)E.h_recv_rows.size();
@@ -738,8 +734,8 @@ extern "C" void cfdp_plan(void)
   E.planned = true;
 }
 
-/* which gradient kernel runs and how its grid walks the tiles.  version 2 = production (gg_tile_pipe_kernel), 3 = the
- * round-1 kernel (side-by-side timing), 1 = one tile per CTA (second, independent implementation for cross-checks);
+/* which gradient kernel runs and how its grid walks the tiles.  version 2 = production (gg_tile_pipe_kernel),
+ * 1 = one tile per CTA (second, independent implementation for cross-checks);
  * chunk = consecutive tiles per CTA; persistent > 0 = that many CTAs walk all tiles, interleaved */
 static void configure_kernel(int version, int chunk, int persistent)
 {
@@ -747,20 +743,17 @@ static void configure_kernel(int version, int chunk, int persistent)
   /* pipelined kernels: one stage [blob | var rows | volumes] per CTA, two CTAs per SM.  The production kernel keeps the
    * var rows at the END of the stage: they must never overlap the rows the previous tile is still storing (one zone per warp) */
   E.pipe.stage_bytes = std::max(E.max_footprint, (uint32_t)((E.block_threads / 32) * CFDP_ZONE_BYTES) + E.max_hvpv);
-  E.pipe4.stage_bytes = E.max_footprint;
   E.kernel_version = version;
   E.chunk = std::max(1, chunk);
   E.persistent = std::max(0, persistent);
-  E.pipe4.block_points = E.block_threads;
-  E.pipe4.split_roles = env_int("CFDP_SPLIT_ROLES", 1);
   const int smem_limit = 227 * 1024 - 256;
-  if ((E.kernel_version == 2 || E.kernel_version == 3) && (int)E.pipe.stage_bytes > smem_limit) {
+  if (E.kernel_version == 2 && (int)E.pipe.stage_bytes > smem_limit) {
     fprintf(stderr, "cfdp: pipelined kernel needs %u B of shared memory per stage, falling back to the one-tile-per-CTA kernel "
                     "(lower CFDP_TILE_POINTS to avoid this)\n", E.pipe.stage_bytes);
     E.kernel_version = 1;
   }
   ASSERT(E.smem_v1 <= smem_limit);
-  E.smem_bytes = E.kernel_version == 2 ? (int)E.pipe.stage_bytes : (E.kernel_version == 3 ? (int)E.pipe4.stage_bytes : E.smem_v1);
+  E.smem_bytes = E.kernel_version == 2 ? (int)E.pipe.stage_bytes : E.smem_v1;
   CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
   CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_v1));
   if (E.kernel_version == 2) {
@@ -777,16 +770,13 @@ static void configure_kernel(int version, int chunk, int persistent)
       CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
       CUDA_CHECK(cudaFuncSetAttribute(ggk::gg_tile_pipe_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
     }
-  } else if (E.kernel_version == 3) {
-    CUDA_CHECK(cudaFuncSetAttribute(ggk4::gg_tile_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
-    CUDA_CHECK(cudaFuncSetAttribute(ggk4::gg_tile_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E.smem_bytes));
   }
 }
 
 extern "C" int cfdp_set_kernel(int version, int chunk, int persistent)
 {
   Engine &E = g_eng;
-  if (!E.committed || version < 1 || version > 3) return -1;
+  if (!E.committed || version < 1 || version > 2) return -1;
   cfdp_device_synchronize();
   configure_kernel(version, chunk, persistent);
   return E.kernel_version;
@@ -848,7 +838,7 @@ extern "C" void cfdp_commit(void)
   E.region0_doubles = (int)align_up((size_t)std::max(E.max_nfaces * 3, E.max_npts * CFDP_DIM2), 2);
   E.smem_v1 = (int)((size_t)E.region0_doubles * 8 + align_up((size_t)E.max_nloc * NGRAD * 8, 16));
   CUDA_CHECK(cudaMalloc(&E.d_progress, 64)); CUDA_CHECK(cudaMemset(E.d_progress, 0, 64)); E.progress_target = 0;
-  if (env_int("CFDP_PHASE_PROF", 0)) { CUDA_CHECK(cudaMalloc(&E.pipe.prof, 8 * sizeof(unsigned long long))); CUDA_CHECK(cudaMemset(E.pipe.prof, 0, 8 * sizeof(unsigned long long))); E.pipe4.prof = E.pipe.prof; }
+  if (env_int("CFDP_PHASE_PROF", 0)) { CUDA_CHECK(cudaMalloc(&E.pipe.prof, 8 * sizeof(unsigned long long))); CUDA_CHECK(cudaMemset(E.pipe.prof, 0, 8 * sizeof(unsigned long long))); }
   E.fused_signal = env_int("CFDP_FUSED_SIGNAL", 1);
   configure_kernel(env_int("CFDP_KERNEL", 2), env_int("CFDP_CHUNK", 8), env_int("CFDP_PERSISTENT", 0));
 
@@ -1223,6 +1213,7 @@ static void run_iteration(int variant)
   if (variant != CFDP_COMM_FREE && use_direct(variant)) { run_iteration_direct(); return; }
   if (variant == CFDP_COMM_FREE || !have_exchange()) {
     launch_gradient(0, E.ntiles, E.s_comp);                       /* gradients.c:150-165 */
+    E.last_transport = 0;
   } else if (!overlap) {
     launch_gradient(0, E.ntiles, E.s_comp, 0, true);              /* bulk synchronous: compute (packing on the way, threads.c:187-249), then exchange (exchange_data_mpi.c:199-284) */
     if (E.timeline_ek) CUDA_CHECK(cudaEventRecord(E.timeline_ek, E.s_comp));
@@ -1725,7 +1716,7 @@ extern "C" void cfdp_finalize(void)
     delete d;
   }
   E.doms.clear(); E.d_rowmap.clear(); E.point_of_row.clear(); E.peers.clear(); E.send_rows_of.clear(); E.recv_rows_of.clear();
-  if (E.pipe.prof) { cudaFree(E.pipe.prof); E.pipe.prof = nullptr; E.pipe4.prof = nullptr; }
+  if (E.pipe.prof) { cudaFree(E.pipe.prof); E.pipe.prof = nullptr; }
   if (E.d_progress) { cudaFree(E.d_progress); E.d_progress = nullptr; }
   e2e_release();
   if (E.have_device) { /* a later cfdp_configure() may name another device: nothing of this one survives */

@@ -28,9 +28,8 @@
 #include <stdint.h>
 #include "common.h"
 
-#define CFDP_MAX_HALO_POS 1024  /* halo positions of a tile (shared-memory index list of the prefetcher) */
+#define CFDP_MAX_HALO_POS 1024  /* bound on the halo positions of a tile (sanity check at commit) */
 #define CFDP_MAX_CHUNK 64      /* tiles per CTA */
-#define CFDP_MAX_GATHER_PER_THREAD 24 /* 8-byte cp.async a thread issues per tile for the halo gather (measured safe) */
 #define CFDP_MAX_EXPORT 256    /* export rows of a tile kept in shared memory (longer lists are read from global memory) */
 
 namespace ggk {
@@ -191,9 +190,9 @@ struct PipeLayout {
   unsigned long long *prof;        /* optional: SM cycles of thread 0 summed over tiles: [0] wait for data, [1] face walk, [2] rest, [4] tiles */
   unsigned long long *progress;    /* counts finished boundary tiles (tile index < nsignal): the early-send trigger the comm stream waits on */
   int nsignal;
-  int variant;                     /* experiment switches (CFDP_VARIANT): 1 = L2 prefetch of the next tile's late-fetched blob head at the start of
-                                    * the face walk, 2 = of all of the next tile, 4 = issued by the last warp instead of warp 0,
-                                    * 8 = early fetch after warp 0's store, 16 = prefetch the whole blob, 32 = early fetch issued by four warps */
+  int variant;                     /* CFDP_VARIANT: 1 (default) = L2 prefetch of the next tile's late-fetched blob head at the start of the
+                                    * face walk, 2 = of all of the next tile, 0 = none */
+  int spread_m, spread_nb;         /* > 1: boundary tile q < spread_nb is walked at position q * spread_m (see tile_of) */
   int tile_base;                   /* global index of this launch's first tile */
   int nexport;                     /* global tiles [0, nexport) write their export rows (fused pack / direct halo stores); 0 = off */
   const uint32_t *exp_off, *exp_src, *exp_dst; /* per boundary tile: (tile-local point | destination array << 16) -> row of that array */
@@ -338,7 +337,17 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
   if (count > L.maxcount) count = L.maxcount;
   const uint32_t sbase = smem_u32(smem), bar = smem_u32(&full);
   const uint64_t pol_stream = l2_policy_evict_first();
-  auto tile_of = [&](int i) { return (int)(first + (long long)i * L.istride); };
+  /* position k of the walk -> tile.  Normally the identity (boundary tiles come first in the tile list: early send).  With direct
+   * halo stores nothing waits for the boundary as a whole, and a burst of boundary tiles at the start of the kernel only congests
+   * NVLink with their small stores: the spread_nb boundary tiles are then dealt out evenly, one at the head of every run of
+   * spread_m positions (CFDP_DIRECT_SPREAD) */
+  auto tile_of = [&](int i) {
+    const long long k = first + (long long)i * L.istride;
+    if (L.spread_m <= 1) return (int)k;
+    const long long q = k / L.spread_m, r = k - q * L.spread_m;
+    if (q >= L.spread_nb) return (int)k;                              /* past the mixed part: the remaining interior tiles in order */
+    return r == 0 ? (int)q : (int)(L.spread_nb + q * (L.spread_m - 1) + (r - 1));
+  };
 
   /* descriptor (and export bounds) of this CTA's tile i -> ring slot i & 3, asynchronously */
   auto prefetch_desc = [&](int i) {
@@ -418,25 +427,21 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
       }
     }
     cp_async_commit();
-    if (L.variant & 3) {
-      /* the next tile's bytes are asked into L2 now, so that its bulk copies (issued once this tile's walk is over, the
-       * blob head only after the result rows have left) find them there instead of paying a DRAM round trip */
-      const int pw = (L.variant & 4) ? (nthr >> 5) - 1 : 0;
-      if (has_next && warp == pw && lane == 0) {
-        const TileDesc &pd = s_desc[(i + 1) & 3];
-        const unsigned char *src = blob + pd.blob_off();
-        const uint32_t oc = CFDP_HALO_BASE((uint32_t)npts) * CFDP_ROW_BYTES;
-        if (L.variant & 2) {
-          const uint32_t ne = CFDP_HALO_BASE((uint32_t)pd.npts);
-          bulk_prefetch_l2(src, (pd.blob_bytes + 15u) & ~15u);
-          bulk_prefetch_l2(hvar + (size_t)pd.row0 * NGRAD, ne * (NGRAD * 8));
-          if (pd.nhalo) bulk_prefetch_l2(hhalo + (size_t)pd.hrow0 * NGRAD, (uint32_t)pd.nhalo * (NGRAD * 8));
-          bulk_prefetch_l2(pvol + pd.row0, ne * 8);
-        } else if (L.variant & 16) {
-          bulk_prefetch_l2(src, (pd.blob_bytes + 15u) & ~15u);
-        } else {
-          bulk_prefetch_l2(src, ((oc < pd.blob_bytes ? oc : pd.blob_bytes) + 15u) & ~15u);
-        }
+    if (L.variant && has_next && tid == 0) {
+      /* the bytes of the next tile that can only be fetched late (the head of its blob, once this tile's result rows have
+       * left the stage) are asked into L2 now: their bulk copies then cost an L2 round trip instead of a DRAM one
+       * (+5.5 .. 7 %).  variant 2 asks for all of the next tile: measured slower than the head alone */
+      const TileDesc &pd = s_desc[(i + 1) & 3];
+      const unsigned char *src = blob + pd.blob_off();
+      const uint32_t oc = CFDP_HALO_BASE((uint32_t)npts) * CFDP_ROW_BYTES;
+      if (L.variant == 2) {
+        const uint32_t ne = CFDP_HALO_BASE((uint32_t)pd.npts);
+        bulk_prefetch_l2(src, (pd.blob_bytes + 15u) & ~15u);
+        bulk_prefetch_l2(hvar + (size_t)pd.row0 * NGRAD, ne * (NGRAD * 8));
+        if (pd.nhalo) bulk_prefetch_l2(hhalo + (size_t)pd.hrow0 * NGRAD, (uint32_t)pd.nhalo * (NGRAD * 8));
+        bulk_prefetch_l2(pvol + pd.row0, ne * 8);
+      } else {
+        bulk_prefetch_l2(src, ((oc < pd.blob_bytes ? oc : pd.blob_bytes) + 15u) & ~15u);
       }
     }
 
@@ -485,22 +490,7 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
     TileDesc nd = td;
     if (has_next) { /* early fetch of the next tile: runs under the staging / store of this one */
       nd = s_desc[(i + 1) & 3];
-      if (L.variant & 32) {
-        /* the four requests leave from four warps: the warp that issues them all reaches its own store (and the late
-         * fetch of its zone, the last bytes the next tile waits for) about a thousand cycles after the others */
-        const int nwp = nthr >> 5;
-        const uint32_t ne = CFDP_HALO_BASE((uint32_t)nd.npts);
-        const uint32_t nv = ne * (NGRAD * 8), nh = (uint32_t)nd.nhalo * (NGRAD * 8), np = ne * 8;
-        const uint32_t a_hv = sbase + stage_hvar_off(L.stage_bytes, nd.npts, nd.nhalo);
-        if (tid == 0) {
-          const uint32_t hole = ((uint32_t)nd.nhalo * 4u + 15u) & ~15u;
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nd.blob_bytes - hole + nv + nh + np) : "memory");
-          blob_fetch(nd, out_cover < nd.blob_bytes ? out_cover : nd.blob_bytes, nd.blob_bytes);
-        }
-        if (tid == 32 * min(1, nwp - 1)) bulk_g2s_a(a_hv, hvar + (size_t)nd.row0 * NGRAD, nv, bar, pol_stream);
-        if (tid == 32 * min(2, nwp - 1) && nh) bulk_g2s_a(a_hv + nv, hhalo + (size_t)nd.hrow0 * NGRAD, nh, bar, pol_stream);
-        if (tid == 32 * min(3, nwp - 1)) bulk_g2s_a(sbase + stage_pvol_off(L.stage_bytes, nd.npts), pvol + nd.row0, np, bar, pol_stream);
-      } else if (tid == 0 && !(L.variant & 8)) bulk_early(nd, out_cover < nd.blob_bytes ? out_cover : nd.blob_bytes);
+      if (tid == 0) bulk_early(nd, out_cover < nd.blob_bytes ? out_cover : nd.blob_bytes);
     }
     long long q1 = 0, q2 = 0, q3 = 0;
     if (L.prof && tid == 0) q1 = clock64();
@@ -518,8 +508,6 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
       if (lane == 0) {
         bulk_s2g(grad + ((size_t)td.row0 + 32u * warp) * (NGRAD * 3), sbase + CFDP_ZONE_BYTES * (uint32_t)warp, rows_w * CFDP_ROW_BYTES, pol_stream);
         bulk_commit();
-        /* variant 8: thread 0 requests the next tile only now, while the store engine reads its zone */
-        if (tid == 0 && has_next && (L.variant & 8)) bulk_early(nd, out_cover < nd.blob_bytes ? out_cover : nd.blob_bytes);
       }
     }
     if (L.prof && tid == 0) q2 = clock64();

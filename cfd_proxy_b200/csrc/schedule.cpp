@@ -493,8 +493,8 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
   const bool place_by_bank = opt.bank_placement != 0;
   std::vector<std::vector<unsigned char>> ftile_bytes(opt.flux_blob ? (size_t)ntiles : 0);
   out.ftile_nfaces.assign(opt.flux_blob ? (size_t)ntiles : 0, 0); out.ftile_nhalo = out.ftile_nfaces; out.ftile_maxdeg = out.ftile_nfaces;
-  long long wf_min_total = 0, wf_est_total = 0;
-#pragma omp parallel reduction(+ : wf_min_total, wf_est_total)
+  long long wf_min_total = 0, wf_est_total = 0, wf_v = 0, wf_n = 0, wf_steps = 0;
+#pragma omp parallel reduction(+ : wf_min_total, wf_est_total, wf_v, wf_n, wf_steps)
   {
     std::vector<int> &lmap = lmap_t[omp_get_thread_num()];
     struct Ent { int tt, p1, p0, face; int nbr; /* tile-local: own i or n + halo k */ int fid; uint32_t sign; };
@@ -901,7 +901,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
           if (!nact) continue;
           int mv = 0, mn = 0;
           for (int c = 0; c < 16; c++) { mv = std::max(mv, cnt_v[c]); mn = std::max(mn, cnt_n[c]); }
-          wf_min_total += 10; wf_est_total += 7 * mv + 3 * mn;
+          wf_min_total += 10; wf_est_total += 7 * mv + 3 * mn; wf_v += mv; wf_n += mn; wf_steps++;
         }
       TB(4);
     }
@@ -910,6 +910,7 @@ void build_schedule(const solver_data *sd, const comm_data *cd, const ScheduleOp
   }
   lap("pass B (placement + emit)");
   out.lds_wavefronts_min = wf_min_total; out.lds_wavefronts_est = wf_est_total;
+  if (prof && wf_steps) fprintf(stderr, "  schedule: half-warp steps %lld, mean depth of the worst bank-pair class: var rows %.3f, normals %.3f\n", wf_steps, (double)wf_v / wf_steps, (double)wf_n / wf_steps);
   if (opt.flux_blob) {
     out.ftile_blob.assign((size_t)ntiles + 1, 0);
     for (int k = 0; k < ntiles; k++) out.ftile_blob[(size_t)k + 1] = out.ftile_blob[k] + ftile_bytes[k].size();

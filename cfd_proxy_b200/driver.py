@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 
 import numpy as np
 
@@ -106,6 +107,7 @@ class Session:
         self.domains: list[HostedDomain] = []
         self._files = []
         self._setup_done = False
+        self.timing = {}       # seconds spent in the setup phases (bench.py reports them)
         Session._active = self
 
     # ---- loading -------------------------------------------------------------------------
@@ -137,6 +139,7 @@ class Session:
         """Generate the hosted domains in memory (no files) and attach them."""
         lib = self.lib
         assert spec.px * spec.py * spec.pz == self.ndomains
+        t0 = time.time()
         for r in self.hosted_ranks():
             d = HostedDomain(r)
             lib.cfdp_init_communication_domain(C.byref(d.cd), r)
@@ -150,6 +153,7 @@ class Session:
                 d.info = dict(global_id=np.ctypeslib.as_array(m.global_id, shape=(m.nall,)).copy())
             lib.cfdp_mesh_free_domain(C.byref(m))
             self.domains.append(d)
+        self.timing["mesh_s"] = round(time.time() - t0, 2)
         return self
 
     # ---- setup ---------------------------------------------------------------------------
@@ -164,14 +168,17 @@ class Session:
 
     def setup(self, device: bool = True):
         lib = self.lib
+        t0 = time.time()
         for d in self.domains:
             lib.compute_communication_tables(C.byref(d.cd))
         for d in self.domains:
             lib.init_threads(C.byref(d.cd), C.byref(d.sd), 1)
+        t1 = time.time()
+        lib.cfdp_plan()                 # host: face schedules, device row numbering, exchange row lists
+        t2 = time.time()
         if device:
-            lib.cfdp_commit()
-        else:
-            lib.cfdp_plan()
+            lib.cfdp_commit()           # device: allocations, uploads, kernel configuration, IPC / NCCL setup
+        self.timing.update(tables_s=round(t1 - t0, 2), plan_s=round(t2 - t1, 2), commit_s=round(time.time() - t2, 2))
         self._setup_done = True
         return self
 

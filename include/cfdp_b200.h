@@ -199,8 +199,8 @@ void cfdp_set_resident(int resident);
  * (bit-identical to the reference run with 1 thread); exact = 0: fused multiply-add */
 void cfdp_set_exact(int exact);
 /* after cfdp_commit: which gradient kernel runs and how its grid walks the tile list.  version 2 = production
- * (gg_tile_pipe_kernel), 1 = one tile per CTA (second, independent implementation used by the tests to cross-check),
- * 3 = the round-1 kernel (side-by-side timing only); chunk = consecutive tiles per CTA; persistent > 0 = that many
+ * (gg_tile_pipe_kernel), 1 = one tile per CTA (second, independent implementation used by the tests to cross-check);
+ * chunk = consecutive tiles per CTA; persistent > 0 = that many
  * CTAs walk all tiles, interleaved.  Returns the version in effect, -1 on error.  Defaults: CFDP_KERNEL / CFDP_CHUNK /
  * CFDP_PERSISTENT or 2 / 8 / 0. */
 int cfdp_set_kernel(int version, int chunk, int persistent);

@@ -139,6 +139,30 @@ def test_var_update_between_calls(session_factory):
         assert bits_differ(d.grad[:dom["nown"]], want[:dom["nown"]]) == 0
 
 
+def test_var_refresh_on_the_device(session_factory):
+    """cfdp_refresh_var / cfdp_set_var_refresh rebuild the per-tile copies of the halo var rows from the device var rows
+    (a solver that changes var on the device): the result of an iteration that starts with the refresh is bit-identical,
+    and the refresh is a real kernel launch with a device time."""
+    spec = M.make_spec((24, 20, 16), (2, 2, 2), order="shuffle", hexfrac=0.25)
+    doms = [M.gen_domain(spec, r) for r in range(8)]
+    want, recv, send = oracle_all(doms, exchange=True)
+    S = session_factory(8, device=0)
+    S.load_spec(spec)
+    S.setup()
+    S.lib.cfdp_set_exact(1)
+    l0 = S.stats().launches
+    assert S.lib.cfdp_refresh_var(2) > 0.0
+    assert S.stats().launches - l0 == 2
+    S.lib.cfdp_set_var_refresh(1)
+    for d in S.domains:
+        d.grad[:] = np.nan
+    S.iterate("mpi_async", 2)
+    S.lib.cfdp_set_var_refresh(0)
+    S.download_grad()
+    for a, d in enumerate(S.domains):
+        assert bits_differ(d.grad, want[a]) == 0
+
+
 def test_large_mesh_properties(session_factory):
     """Full-size properties (no oracle run): linearity in var and exact reproducibility, and the two
     independent kernels agree bit for bit."""

@@ -23,6 +23,9 @@ def main():
     peak, _ = measured_peak()
     for mesh in args:
         head, kcfgs = mesh.split("/")
+        head, _, envs = head.partition("@")          # 256:lex:0@CFDP_PLACE_REFINE=2,CFDP_X=1 : environment of this mesh's schedule build
+        extra = dict(kv.split("=") for kv in envs.split(",") if kv)
+        os.environ.update(extra)
         tile, order, fma, budget, ctas = (head.split(":") + ["0", "2"])[:5]
         os.environ["CFDP_CTAS"] = ctas
         if int(budget):
@@ -66,9 +69,10 @@ def main():
                     S.lib.cfdp_get_phase_profile(buf, 1)
                     nt = max(buf[4], 1)
                     prof = dict(wait=round(buf[0] / nt), walk=round(buf[1] / nt), rest=round(buf[2] / nt), early=round(buf[5] / nt), stage_store=round(buf[6] / nt), wait_read=round(buf[7] / nt))
-                print(json.dumps(dict(mesh=head, kernel=kc, kernel_ms=round(ms, 4), spread=[round(min(r["k"]), 4), round(max(r["k"]), 4)], gfaces=round(st.nfaces / ms / 1e6, 2), frac=round(st.alg_bytes / ms / 1e6 / peak, 4),
+                print(json.dumps(dict(mesh=head, env=extra, kernel=kc, kernel_ms=round(ms, 4), spread=[round(min(r["k"]), 4), round(max(r["k"]), 4)], gfaces=round(st.nfaces / ms / 1e6, 2), frac=round(st.alg_bytes / ms / 1e6 / peak, 4),
                                       async_ms=round(ms_a, 4), bulk_ms=round(ms_b, 4), boundary_tiles=st.nboundary_tiles, smem=st.smem_bytes, tiles=st.ntiles, dup=round(st.tile_faces / st.nfaces, 3),
                                       blob_B_per_face=round(st.blob_bytes / st.nfaces, 2), setup_s=round(setup_s, 1), phase=prof)), flush=True)
+            for k in extra: os.environ.pop(k, None)
             if os.environ.get("KBENCH_FLUX"):   # KBENCH_FLUX=0,1,2,3: pseudo-flux kernel variants (CFDP_FLUX_VARIANT), interleaved
                 fv = os.environ["KBENCH_FLUX"].split(",")
                 S.flux_iterate(3)

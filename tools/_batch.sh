@@ -1,5 +1,5 @@
 set -x
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-(time $TR --master-port 29521 bench.py --gpus 8 --mpoints 256 --steps 20 --warmup 5) > gpurun_out/r03_bench256_8gpu.log 2>&1
-$TR --master-port 29522 tools/f6like_configs.py gpu 24 > gpurun_out/r03_config3_f6like24_8gpu.log 2>&1
-(timeout 600 python -m pytest tests/test_multigpu.py -x -q -k "8-24 or 4-12" 2>&1 | tail -3) > gpurun_out/r03_mg8.log 2>&1
+(time python bench.py) > gpurun_out/r04_bench64.log 2>&1
+T="python tools/ncu_target.py 64 lex 2.8.0 6"
+$T > gpurun_out/r04_plain_target.log 2>&1 &&
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gg_tile_pipe -s 4 -c 2 --csv --log-file gpurun_out/r04_traffic64.csv $T > gpurun_out/r04_ncu_traffic.log 2>&1

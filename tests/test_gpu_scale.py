@@ -160,3 +160,41 @@ def test_one_sided_entry_points_with_several_domains(session_factory, monkeypatc
                 fn(C.byref(d.cd), C.byref(d.sd), int(it == 1))
         for a, d in enumerate(S.domains):
             assert bits_differ(d.grad, want[a]) == 0, f"{name}: domain {a}"
+
+
+@pytest.mark.parametrize("env,tile,variant,loopback", [
+    ({"CFDP_VARIANT": "0"}, 256, "mpi_async", 0),                 # no L2 prefetch of the next tile
+    ({"CFDP_VARIANT": "2"}, 256, "mpi_async", 0),                 # all of the next tile asked into L2
+    ({"CFDP_CTAS": "3"}, 128, "mpi_async", 0),                    # three CTAs of <= 160 threads per SM
+    ({"CFDP_CTAS": "4"}, 128, "gaspi_async", 1),                  # four CTAs of 128 threads per SM, direct halo stores
+    ({"CFDP_DIRECT_SPREAD": "60"}, 64, "gaspi_async", 1),         # boundary tiles dealt out over the walk (direct stores only)
+    ({"CFDP_FLUX_VARIANT": "0"}, 256, "mpi_async", 0),            # pseudo flux without the L2 row prefetch
+    ({"CFDP_FLUX_VARIANT": "3"}, 256, "mpi_async", 0),
+])
+def test_optional_kernel_shapes_bit_identical(session_factory, monkeypatch, env, tile, variant, loopback):
+    """The switches that are off by default (measured slower, profiles/README.md) stay correct: same bits as the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.setenv("CFDP_CHUNK", "3")
+    if loopback:
+        monkeypatch.setenv("CFDP_LOOPBACK", "1")
+    spec = M.make_spec((28, 24, 20), (2, 2, 2), order="shuffle", brick=4, hexfrac=0.3)
+    doms = [M.gen_domain(spec, r) for r in range(8)]
+    want, recv, send = oracle_all(doms)
+    want_flux = [O.psd_flux(d, want[a], is_send=O.is_send_mask(d, send[a]), order=1) for a, d in enumerate(doms)]
+    S = session_factory(8, device=0, tile_points=tile)
+    S.load_spec(spec)
+    S.setup()
+    for d in S.domains:
+        d.grad[:] = np.nan
+        d.psd_flux[:] = np.nan
+    S.upload_grad()
+    S.set_flux(True)
+    S.iterate(variant, 3)
+    S.set_flux(False)
+    S.download_grad()
+    S.download_flux()
+    for a, d in enumerate(S.domains):
+        nown = doms[a]["nown"]
+        assert bits_differ(d.grad, want[a]) == 0, f"domain {a}"
+        assert bits_differ(d.psd_flux[:nown], want_flux[a][:nown]) == 0

@@ -1,3 +1,2 @@
 set -x
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1"
-$TR --master-port 29541 tools/f6like_configs.py gpu 24 > gpurun_out/r04_config3_f6like24_4gpu.log 2>&1
+(timeout 600 python -m pytest tests/test_gpu_scale.py tests/test_gpu_parity.py -x -q -k "optional_kernel or var_refresh" 2>&1 | tail -5) > gpurun_out/r04_t1.log 2>&1

@@ -3,6 +3,8 @@
     oracle/_ref/ref_harness) -- runs everywhere, including the GPU box,
   * a live run of oracle/_ref when it has been built in this tree (the container with /root/reference).
 The reference itself ships no golden vectors or numerical tests."""
+import os
+
 import numpy as np
 import pytest
 
@@ -113,3 +115,22 @@ def test_live_reference_run(tmp_path, threads):
             assert (err <= 1e-12 * np.abs(grads[a][:d["nown"]]) + 64 * EPS * scale).all()
         for k in send[a]:
             assert np.array_equal(ref[a]["sendindex"][k], send[a][k])
+
+
+@pytest.mark.skipif(not (O.have_ref() and os.path.exists(os.path.join(O.REF_DIR, "hybrid.f6.exe")) and os.path.exists(os.path.join(O.REF_DIR, "mesh_tool"))),
+                    reason="oracle/_ref not built (needs /root/reference)")
+def test_config1_reference_main_reports_its_timings():
+    """BASELINE config 1 (tools/f6like_configs.py ref): the UNMODIFIED hybrid.f6.exe, 12 ranks over the shm-MPI shim, on the F6-like
+    stand-in written by the standalone mesh_tool, prints its own report (solver.c:246-313) with non-zero MPI timings."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "f6like_configs.py"), "ref", "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "*** SUCCESS" in r.stdout
+    t = dict(re.findall(r"^\s*(\w+):\s+([0-9.]+)\s*$", r.stdout, flags=re.M))
+    assert int(float(t["nProc"])) == 12
+    for k in ("comm_free", "exchange_dbl_mpi_bulk_sync", "exchange_dbl_mpi_early_recv", "exchange_dbl_mpi_async"):
+        assert float(t[k]) > 0.0, k
+    assert float(t["exchange_dbl_gaspi_async"]) == 0.0      # MPI-only build (USE_GASPI off)

@@ -147,7 +147,7 @@ class Session:
             rc = lib.cfdp_mesh_gen_domain(C.byref(spec), r, C.byref(m))
             if rc != 0:
                 raise RuntimeError(f"cfdp_mesh_gen_domain rc={rc}")
-            lib.cfdp_attach_mesh(C.byref(m), C.byref(d.cd), C.byref(d.sd))
+            lib.cfdp_attach_mesh_take(C.byref(m), C.byref(d.cd), C.byref(d.sd))
             lib.cfdp_mesh_fill_var(C.byref(m), seed, d.sd.var)
             if keep_info:
                 d.info = dict(global_id=np.ctypeslib.as_array(m.global_id, shape=(m.nall,)).copy())

@@ -131,7 +131,7 @@ EXPORTED = [
     "cfdp_iterate", "cfdp_step_e2e", "cfdp_device_synchronize", "cfdp_finalize", "cfdp_get_stats",
     "cfdp_get_schedule", "cfdp_get_tile", "cfdp_get_tile_blob", "cfdp_get_pack_list", "cfdp_get_unpack_list", "cfdp_get_sendbuf",
     "cfdp_mesh_num_domains", "cfdp_mesh_count_faces_global", "cfdp_mesh_gen_domain",
-    "cfdp_mesh_free_domain", "cfdp_mesh_fill_var", "cfdp_mesh_var_value", "cfdp_attach_mesh",
+    "cfdp_mesh_free_domain", "cfdp_mesh_fill_var", "cfdp_mesh_var_value", "cfdp_attach_mesh", "cfdp_attach_mesh_take",
 ]
 
 _lib = None
@@ -218,5 +218,6 @@ def load() -> C.CDLL:
     sig("cfdp_mesh_fill_var", None, P(MeshDomain), C.c_ulonglong, c_dbl_p)
     sig("cfdp_mesh_var_value", C.c_double, C.c_ulonglong, C.c_longlong, C.c_int)
     sig("cfdp_attach_mesh", None, P(MeshDomain), cd_p, sd_p)
+    sig("cfdp_attach_mesh_take", None, P(MeshDomain), cd_p, sd_p)
     _lib = lib
     return lib

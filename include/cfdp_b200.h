@@ -307,6 +307,8 @@ double cfdp_mesh_var_value(unsigned long long seed, long long gid, int eq);
 /* fill sd/cd from an in-memory domain exactly as read_solver_data + init_solver_data +
  * read_communication_data would from its NetCDF file (arrays are copied) */
 void cfdp_attach_mesh(const cfdp_mesh_domain *m, comm_data *cd, solver_data *sd);
+/* the same without copies: the face and volume arrays of *m change hands (m keeps the rest; free it as usual) */
+void cfdp_attach_mesh_take(cfdp_mesh_domain *m, comm_data *cd, solver_data *sd);
 
 #ifdef __cplusplus
 }

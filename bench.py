@@ -44,14 +44,39 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _code_only(text: str) -> str:
+    """C/C++ source without comments and without whitespace (string and character literals are kept verbatim)."""
+    out, i, n = [], 0, len(text)
+    while i < n:
+        c = text[i]
+        if c == "/" and i + 1 < n and text[i + 1] == "/":
+            i = text.find("\n", i)
+            i = n if i < 0 else i
+        elif c == "/" and i + 1 < n and text[i + 1] == "*":
+            j = text.find("*/", i + 2)
+            i = n if j < 0 else j + 2
+        elif c in "\"'":
+            j = i + 1
+            while j < n and text[j] != c:
+                j += 2 if text[j] == "\\" else 1
+            out.append(text[i:j + 1])
+            i = j + 1
+        elif c.isspace():
+            i += 1
+        else:
+            out.append(c)
+            i += 1
+    return "".join(out)
+
+
 def kernel_src_sha():
-    """Hash of the sources the gradient kernel and its schedule are built from: an ncu traffic capture is only quoted
-    for the build it was taken from."""
+    """Hash of the CODE (comments and whitespace stripped) the gradient kernel and its schedule are built from: an ncu
+    traffic capture is only quoted for the build it was taken from."""
     import hashlib
     h = hashlib.sha256()
     for f in ("gg_kernels.cuh", "engine.cu", "schedule.cpp", "common.h"):
-        with open(os.path.join(ROOT, "cfd_proxy_b200", "csrc", f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(ROOT, "cfd_proxy_b200", "csrc", f), "r", encoding="utf-8", errors="replace") as fh:
+            h.update(_code_only(fh.read()).encode())
     return h.hexdigest()[:16]
 
 

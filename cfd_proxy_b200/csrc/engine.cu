@@ -3,20 +3,24 @@
  * Green-Gauss tile kernel (sm_100a), device pack / unpack, and the halo exchange pipeline.
  *
  * Reference functions replaced:
- *   private_compute_gradients_gg ............ src/gradients.c:25-147   -> gg_tile_kernel
+ *   private_compute_gradients_gg ............ src/gradients.c:25-147   -> gg_tile_pipe_kernel (gg_kernels.cuh); gg_tile_kernel = second implementation
  *   compute_gradients_gg_<variant> .......... src/gradients.c:150-335  -> run_iteration()
  *   private_get_color_and_exchange .......... src/rangelist.c:838-889  -> stream/event pipeline
- *   initiate_thread_comm_mpi_send / _pack ... src/threads.c:187-346    -> boundary tiles first, pack on the comm stream
- *   exchange_dbl_copy_in / copy_out ......... src/threads.c:791-869    -> rows_gather / rows_scatter kernels
+ *   initiate_thread_comm_mpi_send / _pack ... src/threads.c:187-346    -> boundary tiles first; pack fused into the kernel (export lists);
+ *                                                                        gaspi_async on several GPUs: direct stores into peer memory
+ *   exchange_dbl_copy_in / copy_out ......... src/threads.c:791-869    -> fused pack / rows_copy_kernel (unpack, permutations)
  *   exchange_dbl_mpi_send/_post_recv/_bulk_sync/_early_recv/_async
  *                                             src/exchange_data_mpi.c:96-543 -> grouped ncclSend/ncclRecv per peer GPU
+ *   exchange_dbl_gaspi_write / mpidma_write . src/exchange_data_gaspi.c:105-151, exchange_data_mpidma.c:93-127
+ *                                                                     -> CUDA-IPC put + notify, or direct halo stores (run_iteration_direct)
  *   init_threads ............................ src/threads.c:730-788    -> registers the domain; cfdp_commit builds the schedule
  *
  * Layout in HBM (one process = one GPU, all hosted domains concatenated):
- *   var  [rows][7]  f64   rows = for each domain: tiles (boundary tiles first, each padded to 16 rows), then ghosts
+ *   var  [rows][7]  f64   0.5 * var; rows = for each domain: tiles (boundary tiles first, each padded to 16 rows), then ghosts
+ *   hhalo           per tile: the var rows of its halo points, contiguous (halo_pack_kernel, rebuilt when var changes)
  *   grad [rows][21] f64
  *   pvol [rows]     f64
- *   blob            tile blobs (normals, halo rows, ELL adjacency), see common.h
+ *   blob            tile blobs (normals, halo row list, ELL adjacency), see common.h
  *   tiles           TileDesc list: boundary tiles of all domains, then interior tiles of all domains
  */
 #include <cuda_runtime.h>

@@ -9,10 +9,11 @@
  *
  * gg_tile_pipe_kernel (the production kernel): two CTAs per SM, each walking a chunk of consecutive tiles through
  * one shared-memory stage.  Per tile ONE elected thread issues the TMA bulk copies (cp.async.bulk global->shared,
- * mbarrier complete_tx): the tile blob (face normals read once, halo row list, ELL adjacency), the contiguous hvar
- * rows and volumes of the tile's own points; all threads gather the hvar rows of the tile's halo points with 8-byte
- * cp.async (LDGSTS) tracked by the same mbarrier.  The next tile is fetched as soon as the face walk of the
- * current one is over, the result rows leave through one TMA bulk store: HBM is only touched by asynchronous copies.
+ * mbarrier complete_tx): the tile blob (face normals read once, ELL adjacency), the contiguous hvar rows and volumes
+ * of the tile's own points and the tile's PACKED halo rows (halo_pack_kernel writes them when var is uploaded; there
+ * is no gather inside the kernel).  The next tile is fetched as soon as the face walk of the current one is over --
+ * the part of it that must wait for the result rows to leave is asked into L2 beforehand (cp.async.bulk.prefetch.L2)
+ * -- and the result rows leave through one TMA bulk store per warp: HBM is only touched by asynchronous copies.
  *
  * Arithmetic modes
  *   EXACT = true : separate IEEE multiply and add in the reference's order.  The device holds
@@ -47,7 +48,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 /* L2 eviction policies: the tile blobs and the gradient rows are touched once per iteration (evict first);
- * the hvar rows are read again by the neighbouring tiles' halo gathers (evict last) */
+ * the hvar rows are read again by halo_pack_kernel only (evict last is kept for uploads that repack at once) */
 __device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
   uint64_t p;

@@ -420,6 +420,8 @@ gg_tile_pipe_kernel(const TileDesc *__restrict__ tiles, int ntiles, const unsign
     const bool exp_in_smem = nexp > 0 && nexp <= CFDP_MAX_EXPORT;
     const uint32_t g0 = (nexp > 0 && L.sig_off) ? s_soff[i & 3][0] : 0u;
     const int nsig = (nexp > 0 && L.sig_off) ? (int)(s_soff[i & 3][1] - g0) : 0;   /* <= one entry per peer */
+    /* NOTE: threads 32.. fetch the entries, so direct halo stores need blocks of at least 64 threads (tiles of more than 32
+     * points); smaller tiles are only used by single-GPU tests, where sig_off is null */
     if (tid >= 32 && tid < 32 + nsig) cp_async4(&s_sig[tid - 32], L.sig_ent + g0 + (tid - 32));
     if (exp_in_smem) {
       for (int k = tid; k < nexp; k += nthr) {
